@@ -173,13 +173,24 @@ def eccentric_anomaly_multi_epoch(time_deltas, period, eccentricity, tol=10 ** -
 
 
 def kepler_exact(M, e, iters=60):
-    """Independent check of the root: safeguarded Newton to machine precision (not reference code)."""
+    """Independent check of the root (not reference code): bisection on the folded problem
+    0 <= |M'| <= pi, then three Newton polishes; valid for every e < 1."""
     M = np.asarray(M, dtype=np.float64)
     e = np.broadcast_to(np.asarray(e, dtype=np.float64), M.shape)
-    E = M + e * np.sin(M)
+    turns = np.floor(M / (2 * np.pi) + 0.5)
+    Mr = M - turns * 2 * np.pi
+    a = np.abs(Mr)
+    lo = np.zeros_like(a)
+    hi = np.full_like(a, np.pi)
     for _ in range(iters):
-        E = E - (E - e * np.sin(E) - M) / (1 - e * np.cos(E))
-    return E
+        mid = 0.5 * (lo + hi)
+        below = mid - e * np.sin(mid) - a < 0
+        lo = np.where(below, mid, lo)
+        hi = np.where(below, hi, mid)
+    E = 0.5 * (lo + hi)
+    for _ in range(3):
+        E = E - (E - e * np.sin(E) - a) / (1 - e * np.cos(E))
+    return np.where(Mr < 0, -E, E) + turns * 2 * np.pi
 
 
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,297 @@
+// Per-orbit device functions: inverse-CDF sampling, Kepler solve, radial velocity.
+//
+// Two precisions share the same Philox draws:
+//   * OrbitF32 / *_f32 : the fused hot path.  Works in the variables the formulas need
+//     (log2 M1, x = log10 P/day, orbital phase in turns, cos i) and never materialises P, M1, a.
+//   * *_f64            : the materialised drop-in arrays and the fp64 replay entries; same maps
+//     written in the reference's own units (kg, s, rad).
+//
+// Reference code replaced (file:line in /root/reference):
+//   sample_powerlaw RVMC.py:103-112   sample_masses :121-126   sample_period :128-134
+//   sample_mass_ratio :136-140        sample_eccentricity :148-161   sample_inclination :114-119
+//   sample_orbit_rotation :142-146    sample_time :163-168
+//   calculate_eccentric_anomaly :170-180 (SciPy secant -> closed-form starter + Halley)
+//   calculate_semi_major_axis :182-187, max_orbital_velocity :189-198, binary_radial_velocity :200-212
+#pragma once
+#include "rvmc_constants.h"
+#include "rvmc_math.cuh"
+
+namespace rvmc {
+
+// ---------------------------------------------------------------------------------------------
+// Derived constants of one population (host-computed in double by derive_pop(), abi.cu)
+// ---------------------------------------------------------------------------------------------
+// Power-law inverse CDF  x = min * (a + b*u)^inv,  a = pmax = (max/min)^(power+1), b = 1 - pmax.
+template <typename T>
+struct PowerLaw {
+    T a, b, inv, minv;
+    int kind;   // PowKind of `inv`
+};
+
+template <typename T>
+struct PopT {
+    PowerLaw<T> mass;     // solar masses (2e30 kg)
+    PowerLaw<T> logp;     // x = log10(P/day)
+    PowerLaw<T> q;
+    PowerLaw<T> e_long;   // P > p_mid      (e < 0.9)
+    PowerLaw<T> e_mid;    // p_circ < P <= p_mid (e < 0.5)
+    T x_circ, x_mid;      // log10(4), log10(6): thresholds in x
+    T p_circ_s, p_mid_s;  // the same thresholds in seconds (fp64 path compares like the reference)
+    T log2_mass_min;      // log2(min_mass)
+    T log2_c0;            // log2 of C0 = (2 pi G Msun / day)^(1/3) * 1e-3  [km/s]
+    T sigma_dyn;
+    T guard_amp;          // fp64 guard: refine when sqrt(1-e^2)/(1-e cos E)^2 exceeds this
+};
+typedef PopT<float> PopF32;
+typedef PopT<double> PopF64;
+
+// ---------------------------------------------------------------------------------------------
+// fp32 hot path
+// ---------------------------------------------------------------------------------------------
+struct OrbitF32 {
+    float log2m;   // log2(M1 / Msun_ref)
+    float x;       // log10(P / day)
+    float phase;   // orbital phase in turns, wrapped to [-0.5, 0.5]  (M = 2 pi phase)
+    float uphase;  // the raw draw in [0,1): time = uphase * P
+    float q;
+    float e;
+    float cosi, sini;
+    float wturn;   // omega / 2 pi
+};
+
+RVMC_HD float powerlaw_f32(const PowerLaw<float>& pl, float u) {
+    return pl.minv * pow_kind(fmaf(pl.b, u, pl.a), pl.inv, pl.kind);
+}
+
+// Orbit of `item` from Philox blocks ORBIT_A/ORBIT_B (7 of the 8 words are used).
+RVMC_HD OrbitF32 sample_orbit_f32(const PopF32& P, const u32x4& wa, const u32x4& wb) {
+    OrbitF32 o;
+    // mass: only log2 m is needed downstream
+    {
+        const float p = fmaf(P.mass.b, u01_f32(wa.x), P.mass.a);
+        o.log2m = (P.mass.kind == POW_ONE) ? fast_lg2(P.mass.minv * p)
+                                           : fmaf(P.mass.inv, fast_lg2(p), P.log2_mass_min);
+    }
+    o.x = powerlaw_f32(P.logp, u01_f32(wa.y));
+    o.uphase = u01_f32(wa.z);
+    o.phase = o.uphase - rintf(o.uphase);
+    o.q = powerlaw_f32(P.q, u01_f32(wa.w));
+    {
+        const float ue = u01_f32(wb.x);
+        const bool is_long = o.x > P.x_mid;
+        const PowerLaw<float>& pl = is_long ? P.e_long : P.e_mid;
+        const float e = powerlaw_f32(pl, ue);
+        o.e = (o.x > P.x_circ) ? e : 0.0f;
+    }
+    o.cosi = u01_f32(wb.y);
+    o.sini = fast_sqrt((1.0f - o.cosi) * (1.0f + o.cosi));
+    o.wturn = u01_f32(wb.z);
+    return o;
+}
+
+// Semi-amplitude K = q/(1+q) * (2 pi G M1 (1+q) / P)^(1/3) * sin i / sqrt(1-e^2)  [km/s]
+// == RVMC.py:187,197-198,209 rearranged; one ex2 on a sum of log2 terms.
+RVMC_HD float semi_amplitude_f32(const PopF32& P, const OrbitF32& o) {
+    const float third = 0.3333333333333333f;
+    float l = fmaf(third, o.log2m, P.log2_c0);
+    l = fmaf(-1.1073093649624542f, o.x, l);                      // -(log2 10)/3 * x
+    l = fmaf(-0.6666666666666666f, fast_lg2(1.0f + o.q), l);
+    const float ome2 = (1.0f - o.e) * (1.0f + o.e);
+    return fast_ex2(l) * o.q * o.sini * fast_rsqrt(ome2);
+}
+
+// Kepler's equation E - e sin E = M for 0 <= M <= pi (callers fold the sign of M out).
+// Markley (1995) cubic starter (|error| < 5e-4 rad for every e < 1) followed by `iters` Halley
+// steps; the iteration count is a launch-uniform constant, so a warp never diverges here.
+// Returns E and its sin/cos (angle-addition update of the last evaluated pair).
+RVMC_HD float kepler_f32(float M, float e, int iters, float& sE, float& cE, float& resid) {
+    const float pi = 3.14159265358979f;
+    const float ome = 1.0f - e;
+    const float alpha = fmaf(5.026548245743669f * (pi - M), fast_rcp(1.0f + e), 29.608813203268074f) *
+                        0.25841921902300255f;     // (3 pi^2 + 1.6 pi (pi-M)/(1+e)) / (pi^2 - 6)
+    const float d = fmaf(3.0f, ome, alpha * e);
+    const float ad = alpha * d;
+    const float q = fmaf(2.0f * ad, ome, -M * M);
+    const float M2 = M * M;
+    const float r = fmaf(3.0f * ad * (d - ome), M, M2 * M);
+    float w = fabsf(r) + fast_sqrt(fmaf(q * q, q, r * r));
+    w = fast_ex2(0.6666666666666666f * fast_lg2(w));             // w^(2/3)
+    const float den = fmaf(w, w + q, q * q);
+    // E0 = (2 r w / den + M) / d  with a single reciprocal
+    float E = fmaf(2.0f * r, w, M * den) * fast_rcp(den * d);
+    E = (M == 0.0f) ? 0.0f : E;                                   // 0/0 guard at the exact origin
+    float s, c, f = 0.0f;
+    sincos_rad(E, s, c);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        f = fmaf(-e, s, E) - M;
+        const float fp = fmaf(-e, c, 1.0f);
+        const float fpp = e * s;
+        const float dE = -f * fp * fast_rcp(fmaf(fp, fp, -0.5f * f * fpp));
+        E += dE;
+        if (it + 1 < iters) {
+            sincos_rad(E, s, c);
+        } else {
+            // sin/cos(E + dE) from sin/cos(E): |dE| < 1e-3 after the starter
+            const float d2 = dE * dE;
+            const float cd = fmaf(d2, fmaf(d2, 4.1666667e-2f, -0.5f), 1.0f);
+            const float sd = dE * fmaf(d2, -1.6666667e-1f, 1.0f);
+            const float s1 = fmaf(s, cd, c * sd);
+            c = fmaf(c, cd, -s * sd);
+            s = s1;
+        }
+    }
+    sE = s;
+    cE = c;
+    resid = fmaf(-e, s, E) - M;
+    return E;
+}
+
+// fp64 guard: given the fp32 solution, polish E in double and return sin/cos in double.
+RVMC_HD void kepler_refine_f64(double M, double e, double& E, double& sE, double& cE) {
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+        sE = sin(E);
+        cE = cos(E);
+        E -= (E - e * sE - M) / (1.0 - e * cE);
+    }
+    sE = sin(E);
+    cE = cos(E);
+}
+
+// RV / K = cos(nu + omega) + e cos(omega) with the true anomaly taken in closed form
+// (cos nu = (cos E - e)/(1 - e cos E), sin nu = sqrt(1-e^2) sin E/(1 - e cos E)); equal to the
+// 2*atan(sqrt((1+e)/(1-e)) tan(E/2)) form of RVMC.py:211-212.
+RVMC_HD float rv_shape_f32(float e, float sE, float cE, float sw, float cw) {
+    const float rd = fast_rcp(fmaf(-e, cE, 1.0f));
+    const float cnu = (cE - e) * rd;
+    const float snu = fast_sqrt((1.0f - e) * (1.0f + e)) * sE * rd;
+    return fmaf(cnu, cw, fmaf(-snu, sw, e * cw));
+}
+
+// Full single-epoch orbital RV of one sampled orbit [km/s]; `sgn` folds M into [0, pi].
+// n_guard counts lanes that took the fp64 path, n_bad lanes whose residual stayed above 1e-5.
+RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float* K_out, int& guard,
+                           int& bad) {
+    const float K = semi_amplitude_f32(P, o);
+    const float M = 6.283185307179586f * fabsf(o.phase);
+    float sE, cE, resid;
+    const float E = kepler_f32(M, o.e, iters, sE, cE, resid);
+    sE = (o.phase < 0.0f) ? -sE : sE;
+    float sw, cw;
+    sincos_turn(o.wturn, sw, cw);
+    float shape;
+    const float dd = fmaf(-o.e, cE, 1.0f);
+    const float ome2 = (1.0f - o.e) * (1.0f + o.e);
+    // amplification of an error in M into nu: sqrt(1-e^2)/(1-e cos E)^2
+    if (dd * dd * P.guard_amp < fast_sqrt(ome2)) {
+        double E64 = (double)E, s64, c64;
+        const double e64 = (double)o.e;
+        kepler_refine_f64(RVMC_TWO_PI * fabs((double)o.phase), e64, E64, s64, c64);
+        if (o.phase < 0.0f) s64 = -s64;
+        const double rd = 1.0 / (1.0 - e64 * c64);
+        const double cnu = (c64 - e64) * rd;
+        const double snu = sqrt((1.0 - e64) * (1.0 + e64)) * s64 * rd;
+        const double w = RVMC_TWO_PI * (double)o.wturn;
+        shape = (float)(cnu * cos(w) - snu * sin(w) + e64 * cos(w));
+        guard = 1;
+        bad = 0;
+    } else {
+        shape = rv_shape_f32(o.e, sE, cE, sw, cw);
+        guard = 0;
+        bad = (fabsf(resid) > 1e-5f) ? 1 : 0;
+    }
+    if (K_out) *K_out = K;
+    return K * shape;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 path: the same draws in the reference's units
+// ---------------------------------------------------------------------------------------------
+struct OrbitF64 {
+    double primary_mass;    // kg
+    double period;          // s
+    double time;            // s
+    double mass_ratio;
+    double eccentricity;
+    double inclination;     // rad
+    double orbit_rotation;  // rad
+};
+
+RVMC_HD double powerlaw_f64(const PowerLaw<double>& pl, double u) {
+    return pow(pl.a + pl.b * u, pl.inv) * pl.minv;
+}
+
+RVMC_HD OrbitF64 sample_orbit_f64(const PopF64& P, const u32x4& wa, const u32x4& wb) {
+    OrbitF64 o;
+    o.primary_mass = powerlaw_f64(P.mass, u01_f64(wa.x)) * RVMC_MSUN_KG;
+    o.period = RVMC_DAY_S * pow(10.0, powerlaw_f64(P.logp, u01_f64(wa.y)));
+    o.time = u01_f64(wa.z) * o.period;
+    o.mass_ratio = powerlaw_f64(P.q, u01_f64(wa.w));
+    const double ue = u01_f64(wb.x);
+    if (o.period > P.p_mid_s)
+        o.eccentricity = powerlaw_f64(P.e_long, ue);
+    else if (o.period > P.p_circ_s)
+        o.eccentricity = powerlaw_f64(P.e_mid, ue);
+    else
+        o.eccentricity = 0.0;
+    o.inclination = acos(u01_f64(wb.y));
+    o.orbit_rotation = u01_f64(wb.z) * RVMC_TWO_PI;
+    return o;
+}
+
+// Root of E - e sin E = M for any real M, returned on the branch the reference reaches from
+// x0 = M (E in [0, 2 pi) for M in [0, 2 pi)).  Converged to the last bit or two; `resid` lets
+// the caller count failures (SciPy's RuntimeWarning equivalent).
+RVMC_HD double kepler_f64(double M, double e, double& resid) {
+    const double pi = 3.141592653589793;
+    const double turns = floor(M / RVMC_TWO_PI + 0.5);
+    const double Mr = M - turns * RVMC_TWO_PI;            // [-pi, pi]
+    const double a = fabs(Mr);
+    const double ome = 1.0 - e;
+    const double alpha = (3.0 * pi * pi + 1.6 * pi * (pi - a) / (1.0 + e)) / (pi * pi - 6.0);
+    const double d = 3.0 * ome + alpha * e;
+    const double q = 2.0 * alpha * d * ome - a * a;
+    const double r = 3.0 * alpha * d * (d - ome) * a + a * a * a;
+    double w = fabs(r) + sqrt(q * q * q + r * r);
+    w = cbrt(w * w);
+    double E = (a == 0.0) ? 0.0 : (2.0 * r * w / (w * w + w * q + q * q) + a) / d;
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const double s = sin(E), c = cos(E);
+        const double f = E - e * s - a;
+        const double fp = 1.0 - e * c;
+        E -= f * fp / (fp * fp - 0.5 * f * e * s);
+    }
+    resid = E - e * sin(E) - a;
+    E = (Mr < 0.0) ? -E : E;
+    return E + turns * RVMC_TWO_PI;
+}
+
+// RVMC.py:182-212 evaluated as written (semi-major axis, periastron speed, arctan/tan form).
+RVMC_HD double orbit_rv_f64(double primary_mass, double period, double q, double e, double inc,
+                            double omega, double E, double* K_out) {
+    const double a = cbrt(RVMC_G_VALUE * (1.0 + q) * primary_mass * period * period /
+                          (4.0 * 9.869604401089358));
+    const double vmax = q * sqrt(RVMC_G_VALUE * primary_mass * (1.0 + e) / ((1.0 + q) * (1.0 - e) * a)) * 0.001;
+    const double K = vmax / (1.0 + e) * sin(inc);
+    const double nu = 2.0 * atan(sqrt((1.0 + e) / (1.0 - e)) * tan(0.5 * E));
+    if (K_out) *K_out = K;
+    return K * (e * cos(omega) + cos(nu + omega));
+}
+
+// Multi-epoch mean anomaly.  quirk != 0 reproduces RVMC_bias_corr.py:357, whose operator
+// precedence yields ((2 pi t) mod P) / P in [0,1) used as radians; quirk == 0
+// is the physical 2 pi frac(t / P).  Needs fp64: 2 pi t reaches 2e8 s against P down to 1e5 s.
+RVMC_HD double mean_anomaly_epoch_f64(double t, double period, int quirk) {
+    if (quirk) {
+        const double a = RVMC_TWO_PI * t;
+        double m = fmod(a, period);
+        if (m < 0.0) m += period;          // np.mod takes the sign of the divisor
+        return m / period;
+    }
+    const double ph = t / period;
+    return RVMC_TWO_PI * (ph - floor(ph));
+}
+
+}  // namespace rvmc

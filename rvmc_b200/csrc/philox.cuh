@@ -1,0 +1,72 @@
+// Counter-based Philox4x32-10 (Salmon et al., SC'11), kept entirely in registers.
+// Replaces every np.random.* call of the reference (RVMC.py:101,111,119,146,168,224,234,235,
+// 264,265,270,271; RVMC_bias_corr.py:183,264,280,306,328,404).
+//
+// Counter layout: ctr = (item_lo, item_hi, stream, sub), key = (seed_lo, seed_hi).
+// `item` is a GLOBAL index (star of the pool, star slot of a cluster realization, binary of the
+// multi-epoch grid), so a value never depends on which thread, launch or GPU computes it.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RVMC_HD __host__ __device__ __forceinline__
+#else
+#define RVMC_HD inline
+#endif
+
+namespace rvmc {
+
+struct u32x4 {
+    uint32_t x, y, z, w;
+};
+
+RVMC_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+template <int ROUNDS = 10>
+RVMC_HD u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c.x, hi0, lo0);
+        mulhilo32(M1, c.z, hi1, lo1);
+        u32x4 n;
+        n.x = hi1 ^ c.y ^ k0;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k1;
+        n.w = lo0;
+        c = n;
+        k0 += W0;
+        k1 += W1;
+    }
+    return c;
+}
+
+// One block for (item, stream, sub) under a 64-bit seed.
+RVMC_HD u32x4 philox_block(uint64_t seed, uint64_t item, uint32_t stream, uint32_t sub) {
+    u32x4 c;
+    c.x = (uint32_t)item;
+    c.y = (uint32_t)(item >> 32);
+    c.z = stream;
+    c.w = sub;
+    return philox4x32<10>(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// 24-bit uniforms.  Both precisions consume the SAME value u = (w >> 8) * 2^-24 (exact in fp32),
+// so the fp32 fused path and the fp64 materialised path see identical draws.
+RVMC_HD float u01_f32(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-8f; }        // [0,1)
+RVMC_HD double u01_f64(uint32_t w) { return (double)(w >> 8) * 5.9604644775390625e-8; }
+RVMC_HD float u01_open_f32(uint32_t w) { return (float)((w >> 8) + 1u) * 5.9604644775390625e-8f; }  // (0,1]
+RVMC_HD double u01_open_f64(uint32_t w) { return (double)((w >> 8) + 1u) * 5.9604644775390625e-8; }
+
+}  // namespace rvmc

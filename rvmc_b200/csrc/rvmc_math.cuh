@@ -1,0 +1,130 @@
+// Scalar math building blocks of the fp32 hot path.
+//
+// Design rule (DESIGN.md "pipe balance"): the SFU/XU pipe retires 16 lanes/clk/SM against 128
+// for FMA, so sin/cos are evaluated as short FMA polynomials after an exact quadrant reduction
+// (also ~4x more accurate than MUFU.SIN, which matters for the 1e-5 parity bound), and MUFU is
+// kept for lg2 / ex2 / rcp / rsqrt / sqrt only.
+//
+// Every function is __host__ __device__ so tests/hostcheck can compile the SAME source for the
+// CPU and check it against the oracle without a GPU (the approximate MUFU ops are replaced by
+// libm there; results agree to a few ulp).  Product code only ever runs the device side.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "philox.cuh"
+
+namespace rvmc {
+
+// ---- MUFU wrappers --------------------------------------------------------------------------
+RVMC_HD float fast_lg2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return log2f(x);
+#endif
+}
+RVMC_HD float fast_ex2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+RVMC_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+RVMC_HD float fast_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+RVMC_HD float fast_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+}
+
+// p^y for p > 0 with the two exponents the Sana et al. defaults produce special-cased
+// (kind is uniform over a launch: 1 -> y == 1, 2 -> y == 2, 0 -> general lg2/ex2).
+enum PowKind : int { POW_GENERAL = 0, POW_ONE = 1, POW_TWO = 2 };
+RVMC_HD float pow_kind(float p, float y, int kind) {
+    if (kind == POW_ONE) return p;
+    if (kind == POW_TWO) return p * p;
+    return fast_ex2(y * fast_lg2(p));
+}
+
+// ---- sin/cos on [-pi/4, pi/4] (Cephes single-precision minimax coefficients) ----------------
+RVMC_HD void sincos_kernel(float r, float& s, float& c) {
+    const float z = r * r;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(z, ps, -1.6666654611e-1f);
+    s = fmaf(r * z, ps, r);
+    float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(z, pc, 4.166664568298827e-2f);
+    c = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+}
+RVMC_HD void quadrant_fix(int q, float ss, float cc, float& s, float& c) {
+    // rotate (sin, cos) of the reduced angle by q quarter turns
+    const float a = (q & 1) ? cc : ss;
+    const float b = (q & 1) ? ss : cc;
+    s = (q & 2) ? -a : a;
+    c = ((q + 1) & 2) ? -b : b;
+}
+// sin/cos of 2*pi*t for a "turn" t (|t| small, e.g. a uniform draw): the quadrant split
+// t - k/4 is exact in fp32, so the reduced angle carries one rounding only.
+RVMC_HD void sincos_turn(float t, float& s, float& c) {
+    const float k = rintf(4.0f * t);
+    const float r = fmaf(-0.25f, k, t) * 6.283185307179586f;
+    float ss, cc;
+    sincos_kernel(r, ss, cc);
+    quadrant_fix((int)k, ss, cc, s, c);
+}
+// sin/cos of x radians for |x| up to a few pi (two-constant Cody-Waite reduction).
+RVMC_HD void sincos_rad(float x, float& s, float& c) {
+    const float k = rintf(x * 0.6366197723675814f);
+    float r = fmaf(-k, 1.5707962512969971f, x);      // pi/2 high part (24 bits)
+    r = fmaf(-k, 7.549789415861596e-8f, r);          // pi/2 low part
+    float ss, cc;
+    sincos_kernel(r, ss, cc);
+    quadrant_fix((int)k, ss, cc, s, c);
+}
+
+// ---- normals ---------------------------------------------------------------------------------
+// Box-Muller from two Philox words: z0 = r cos(theta), z1 = r sin(theta); replaces
+// np.random.normal (legacy polar method) at every noise site of the reference.
+RVMC_HD void box_muller_f32(uint32_t w1, uint32_t w2, float& z0, float& z1) {
+    const float u1 = u01_open_f32(w1);
+    const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));   // sqrt(-2 ln u1)
+    float s, c;
+    sincos_turn(u01_f32(w2), s, c);
+    z0 = r * c;
+    z1 = r * s;
+}
+RVMC_HD void box_muller_f64(uint32_t w1, uint32_t w2, double& z0, double& z1) {
+    const double u1 = u01_open_f64(w1);
+    const double r = sqrt(-2.0 * log(u1));
+    const double th = RVMC_TWO_PI * u01_f64(w2);
+    z0 = r * cos(th);
+    z1 = r * sin(th);
+}
+
+}  // namespace rvmc
