@@ -27,6 +27,13 @@ extern "C" {
 
 #define RVMC_ABI_VERSION 1
 
+/* the library is built with -fvisibility=hidden: only the entry points below are exported */
+#if defined(__GNUC__)
+#define RVMC_API __attribute__((visibility("default")))
+#else
+#define RVMC_API
+#endif
+
 enum {
     RVMC_OK = 0,
     RVMC_ERR_INVALID = -1,      /* bad argument (message says which)                         */
@@ -103,27 +110,42 @@ typedef struct rvmc_grid_point {
 } rvmc_grid_point;
 
 /* ---- library ---------------------------------------------------------------------------- */
-int rvmc_abi_version(void);
-const char* rvmc_last_error(void);
-void rvmc_pop_defaults(rvmc_pop_params* p);               /* RVMC.py:28-43 defaults            */
+RVMC_API int rvmc_abi_version(void);
+RVMC_API const char* rvmc_last_error(void);
+RVMC_API void rvmc_pop_defaults(rvmc_pop_params* p);               /* RVMC.py:28-43 defaults            */
 /* Device probe: fails with RVMC_ERR_NO_DEVICE when there is no sm_100 device. */
-int rvmc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+RVMC_API int rvmc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+
+/* Measurement aid (bench.py): sustained lane-operations per second of one SM pipe on the current
+ * device -- kind 0 FFMA, 1 MUFU.EX2, 2 IMAD.WIDE.U32, 3 DFMA, 4 a mixed FFMA+ALU+MUFU issue stream.
+ * These are the roofline denominators of a path that is bound by the instruction pipes, not by
+ * HBM or the tensor cores.  Synchronises the device (default stream). */
+RVMC_API int rvmc_pipe_peak(int kind, int iters, double* lane_ops_per_s, double* elapsed_ms);
 
 /* ---- K1: Philox (known-answer / replay) ----------------------------------------------------
  * out[4*i..4*i+3] = Philox4x32-10 block of (item = first_item+i, stream, sub) under `seed`.  */
-int rvmc_philox_blocks(uint64_t seed, uint64_t first_item, int64_t n, uint32_t stream, uint32_t sub,
+RVMC_API int rvmc_philox_blocks(uint64_t seed, uint64_t first_item, int64_t n, uint32_t stream, uint32_t sub,
                        uint32_t* out, void* cuda_stream);
 
 /* ---- K1+K2: materialised population, fp64 (RVMC.__init__ RVMC.py:79-95; BiasCorr twins
  * RVMC_bias_corr.py:207-243).  Fills the non-NULL arrays of `out` for items
  * [first_item, first_item+n); eccentric_anomaly is the converged root for M = 2 pi time/period
- * (RVMC.py:170-180).  *nonconverged (device uint32, may be NULL) is incremented per failure. */
-int rvmc_sample_orbits(const rvmc_pop_params* p, uint64_t seed, uint64_t first_item, int64_t n,
-                       rvmc_orbit_soa out, uint32_t* nonconverged, void* cuda_stream);
+ * (RVMC.py:170-180).  `given_mask` marks arrays that are INPUTS rather than outputs: bit 0 =
+ * primary_mass (mass_dist, RVMC.py:79-82), bit 1 = period (period_dist, :84-87; time and
+ * eccentricity then follow the given periods as at :89,:91), bit 2 = time, bit 3 = eccentricity
+ * (bits 2-3 serve a standalone calculate_eccentric_anomaly on user-edited arrays).
+ * *nonconverged (device uint32, may be NULL) is incremented per failure. */
+#define RVMC_GIVEN_MASS 1u
+#define RVMC_GIVEN_PERIOD 2u
+#define RVMC_GIVEN_TIME 4u
+#define RVMC_GIVEN_ECC 8u
+RVMC_API int rvmc_sample_orbits(const rvmc_pop_params* p, uint64_t seed, uint64_t first_item, int64_t n,
+                       uint32_t given_mask, rvmc_orbit_soa out, uint32_t* nonconverged,
+                       void* cuda_stream);
 
 /* out[i] (+)= mean + sigma * N(0,1) from stream `stream`/`sub`, item first_item+i.
  * Replaces np.random.normal at RVMC.py:101 (cluster_velocities) and :224 (sigma_dyn). */
-int rvmc_normal_f64(uint64_t seed, uint64_t first_item, int64_t n, uint32_t stream, uint32_t sub,
+RVMC_API int rvmc_normal_f64(uint64_t seed, uint64_t first_item, int64_t n, uint32_t stream, uint32_t sub,
                     double mean, double sigma, int accumulate, double* out, void* cuda_stream);
 
 /* ---- K3: Kepler + RV on caller-supplied arrays (the replay/parity entries) ------------------
@@ -131,17 +153,25 @@ int rvmc_normal_f64(uint64_t seed, uint64_t first_item, int64_t n, uint32_t stre
  * rvmc_rv_replay_f64: RVMC.py:182-212 evaluated in fp64 as written.
  * rvmc_rv_replay_f32: the fused path's fp32 arithmetic (closed-form K, starter + Halley, fp64
  *   guard) on the same arrays; eccentric_anomaly is recomputed from time/period, E_out optional. */
-int rvmc_kepler_f64(int64_t n, const double* time, const double* period, const double* eccentricity,
+RVMC_API int rvmc_kepler_f64(int64_t n, const double* time, const double* period, const double* eccentricity,
                     double* E_out, uint32_t* nonconverged, void* cuda_stream);
-int rvmc_rv_replay_f64(int64_t n, rvmc_orbit_soa in, double* rv_out, double* K_out, void* cuda_stream);
-int rvmc_rv_replay_f32(int64_t n, rvmc_orbit_soa in, const rvmc_pop_params* p, float* rv_out,
+RVMC_API int rvmc_rv_replay_f64(int64_t n, rvmc_orbit_soa in, double* rv_out, double* K_out, void* cuda_stream);
+/* The two intermediate public methods of the class, for scripts that call them one by one:
+ * semi_major_axis [m] (RVMC.py:182-187) and max_orbital_velocity [km/s] (:189-198) from the
+ * arrays of `in` (either output may be NULL; vmax uses a_in when given, else its own a), and
+ * binary_radial_velocity (:200-212) for a caller-supplied v_max array. */
+RVMC_API int rvmc_orbit_scales_f64(int64_t n, rvmc_orbit_soa in, const double* a_in, double* a_out,
+                          double* vmax_out, void* cuda_stream);
+RVMC_API int rvmc_rv_from_vmax_f64(int64_t n, rvmc_orbit_soa in, const double* v_max, double* rv_out,
+                          void* cuda_stream);
+RVMC_API int rvmc_rv_replay_f32(int64_t n, rvmc_orbit_soa in, const rvmc_pop_params* p, float* rv_out,
                        float* E_out, uint32_t* counters /* [guard, nonconverged] or NULL */,
                        void* cuda_stream);
 
 /* ---- a15: pool mixing (RVMC.calculate_radial_velocity, RVMC.py:228-236) ---------------------
  * radial_velocities[0:nb) = a without-replacement selection of rv_binary (a keyed Feistel
  * permutation of [0,n)), [nb:n) = with-replacement picks of cluster_velocities; nb=int(n*fbin). */
-int rvmc_mix_pool(uint64_t seed, uint32_t call_id, int64_t n, double fbin, const double* rv_binary,
+RVMC_API int rvmc_mix_pool(uint64_t seed, uint32_t call_id, int64_t n, double fbin, const double* rv_binary,
                   const double* cluster_velocities, double* radial_velocities, void* cuda_stream);
 
 /* ---- a16: finite-pool bootstrap (RVMC.subsample, RVMC.py:262-271) ---------------------------
@@ -149,7 +179,7 @@ int rvmc_mix_pool(uint64_t seed, uint32_t call_id, int64_t n, double fbin, const
  * picks from pool[pool_n] + N(0, meas_err[j]); unweighted std with `ddof` (1 for RVMC.py:271,
  * 0 for findBestDistributions.py:29) or the weighted formula of RVMC.py:263-268.
  * meas_err: device float64[sample_size]. */
-int rvmc_sigma1d_pool(uint64_t seed, uint32_t call_id, const double* pool, int64_t pool_n,
+RVMC_API int rvmc_sigma1d_pool(uint64_t seed, uint32_t call_id, const double* pool, int64_t pool_n,
                       const double* meas_err, int sample_size, int weighted, int ddof,
                       uint64_t first_real, int64_t n_real, double* sigma_out, void* cuda_stream);
 
@@ -159,18 +189,19 @@ int rvmc_sigma1d_pool(uint64_t seed, uint32_t call_id, const double* pool, int64
  * N(0, sigma_dyn) and N(0, meas_err[j]).  Per-star values never reach HBM.
  * meas_err: device float32[sample_size].  counters: device uint64[4] =
  * {binary RVs evaluated, fp64-guard lanes, non-converged lanes, reserved} (accumulated) or NULL. */
-int rvmc_sigma1d_fused(const rvmc_pop_params* p, uint64_t seed, const float* meas_err,
+RVMC_API int rvmc_sigma1d_fused(const rvmc_pop_params* p, uint64_t seed, const float* meas_err,
                        int sample_size, int weighted, int ddof, uint64_t first_real, int64_t n_real,
                        float* sigma_out, uint64_t* counters, void* cuda_stream);
 
 /* Per-slot dump of exactly what rvmc_sigma1d_fused computes for star slots
  * [first_slot, first_slot+n) (slot = realization*sample_size + j). */
-int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const float* meas_err, int sample_size,
+RVMC_API int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const float* meas_err, int sample_size,
                      uint64_t first_slot, int64_t n, rvmc_trace_soa out, void* cuda_stream);
 
 /* ---- K5 fused: multi-epoch Delta-RV + significance (BiasCorr, RVMC_bias_corr.py:406-476) ----
- * Binary b = star*nsamples + sample, samples [first_sample, first_sample+n_samples) of every
- * star.  t_obs: device float64[nstars*max_epochs] (row i holds n_epochs[i] valid entries, s);
+ * Binary (star, sample), samples [first_sample, first_sample+n_samples) of every star; `seed`
+ * keys the orbit draws (the same numbers rvmc_biascorr_sample materialises), `noise_seed` the
+ * measurement errors (a fresh one per calculate_radial_velocities() call).  t_obs: device float64[nstars*max_epochs] (row i holds n_epochs[i] valid entries, s);
  * rv_err: device float32[nstars*max_epochs] per-epoch errors in km/s or NULL (no noise, no
  * detection); mass_mode 0 = IMF (RVMC_bias_corr.py:205-207), 1 = N(masses, mass_errors) (:183),
  * 2 = masses at face value (:190); masses/mass_errors: device float64[nstars], kg.
@@ -179,7 +210,7 @@ int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const float* meas_
  * uint8[nstars*n_samples] (:451-476), rv_out float32[nstars*max_epochs*n_samples] (the noisy
  * radial_velocities, :419-421), counters uint64[4] = {binary-epoch RVs, detected, guard,
  * non-converged} (accumulated), det_per_star uint32[nstars] (accumulated). */
-int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, int nstars, int max_epochs,
+RVMC_API int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int nstars, int max_epochs,
                         const int32_t* n_epochs, const double* t_obs, const float* rv_err,
                         int mass_mode, const double* masses, const double* mass_errors,
                         int quirk_phase, float delta_rv_min, float n_sigma,
@@ -189,27 +220,39 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, int nstars, int
 
 /* Materialised per-binary attribute arrays of BiasCorr (RVMC_bias_corr.py:175-243) for the
  * same (seed, star, sample) indexing as rvmc_biascorr_fused; fp64, layout [nstars][n_samples]. */
-int rvmc_biascorr_sample(const rvmc_pop_params* p, uint64_t seed, int nstars, int mass_mode,
+RVMC_API int rvmc_biascorr_sample(const rvmc_pop_params* p, uint64_t seed, int nstars, int mass_mode,
                          const double* masses, const double* mass_errors, uint64_t first_sample,
-                         int64_t n_samples, rvmc_orbit_soa out, void* cuda_stream);
+                         int64_t n_samples, uint32_t given_mask, rvmc_orbit_soa out, void* cuda_stream);
+
+/* The per-star building blocks of the loop at RVMC_bias_corr.py:414-419 for scripts that call
+ * them one by one.  Row arrays (period, eccentricity, ... of the current star) have n_samples
+ * elements and broadcast over the n_epochs rows of time_deltas / E, as in the reference.
+ * rvmc_kepler_epochs_f64: calculate_eccentric_anomaly(time_deltas) (:348-358);
+ * rvmc_rv_epochs_f64: binary_radial_velocity(eccentric_anomalies_i) (:360-372). */
+RVMC_API int rvmc_kepler_epochs_f64(int n_epochs, int64_t n_samples, const double* time_deltas,
+                           const double* period_row, const double* ecc_row, int quirk_phase,
+                           double* E_out, uint32_t* nonconverged, void* cuda_stream);
+RVMC_API int rvmc_rv_epochs_f64(int n_epochs, int64_t n_samples, const double* E, const double* vmax_row,
+                       const double* ecc_row, const double* incl_row, const double* omega_row,
+                       double* rv_out, void* cuda_stream);
 
 /* fp64 replay of RVMC_bias_corr.py:406-422 on caller-supplied (possibly user-overwritten)
  * attribute arrays [nstars][n_samples]; primary_mass may have row length 1 (mass_cols = 1,
  * RVMC_bias_corr.py:190).  noise (seed, rv_err as above) is optional. */
-int rvmc_biascorr_replay_f64(int nstars, int64_t n_samples, int max_epochs, const int32_t* n_epochs,
+RVMC_API int rvmc_biascorr_replay_f64(int nstars, int64_t n_samples, int max_epochs, const int32_t* n_epochs,
                              const double* t_obs, rvmc_orbit_soa in, int64_t mass_cols,
                              const float* rv_err, uint64_t seed, uint64_t first_sample,
                              int quirk_phase, double* rv_out, double* delta_rv, void* cuda_stream);
 
 /* generate_single_delta_rv (RVMC_bias_corr.py:424-442): noise-only max-min per single star.
  * delta_out float64[nstars*n_singles]. */
-int rvmc_biascorr_singles(uint64_t seed, int nstars, int max_epochs, const int32_t* n_epochs,
+RVMC_API int rvmc_biascorr_singles(uint64_t seed, int nstars, int max_epochs, const int32_t* n_epochs,
                           const float* rv_err, uint64_t first_single, int64_t n_singles,
                           double* delta_out, void* cuda_stream);
 
 /* get_detected_binaries (RVMC_bias_corr.py:451-476) on materialised noisy RVs
  * rv[nstars][max_epochs][n_samples] (fp64). */
-int rvmc_biascorr_detect(int nstars, int64_t n_samples, int max_epochs, const int32_t* n_epochs,
+RVMC_API int rvmc_biascorr_detect(int nstars, int64_t n_samples, int max_epochs, const int32_t* n_epochs,
                          const double* rv, const float* rv_err, double delta_rv_min, double n_sigma,
                          uint8_t* detected, void* cuda_stream);
 
@@ -222,8 +265,8 @@ int rvmc_biascorr_detect(int nstars, int64_t n_samples, int max_epochs, const in
  * hist_out: device uint32[n_points*hist_bins] (counts of the `bin`-wide histogram) or NULL;
  * scratch: device float32[scratch_slots*n_real], scratch_slots = rvmc_grid_scratch_slots().
  * Points are independent: shard them over GPUs by passing each rank its own sub-array. */
-int rvmc_grid_scratch_slots(int device);
-int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* meas_err,
+RVMC_API int rvmc_grid_scratch_slots(int device);
+RVMC_API int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* meas_err,
                   int sample_size, int weighted, int ddof, int64_t n_real, double bin, int hist_bins,
                   rvmc_point_stats* stats_out, float* sigma_out, uint32_t* hist_out, float* scratch,
                   uint64_t* counters, void* cuda_stream);

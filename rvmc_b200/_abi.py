@@ -80,19 +80,24 @@ SIGNATURES = {
     "rvmc_last_error": (C.c_char_p, []),
     "rvmc_pop_defaults": (None, [C.POINTER(PopParams)]),
     "rvmc_device_info": (_I, [_I] + [C.POINTER(C.c_int)] * 4),
+    "rvmc_pipe_peak": (_I, [_I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rvmc_philox_blocks": (_I, [_U64, _U64, _I64, _U32, _U32, _VP, _VP]),
-    "rvmc_sample_orbits": (_I, [C.POINTER(PopParams), _U64, _U64, _I64, OrbitSoA, _VP, _VP]),
+    "rvmc_sample_orbits": (_I, [C.POINTER(PopParams), _U64, _U64, _I64, _U32, OrbitSoA, _VP, _VP]),
     "rvmc_normal_f64": (_I, [_U64, _U64, _I64, _U32, _U32, _D, _D, _I, _VP, _VP]),
     "rvmc_kepler_f64": (_I, [_I64, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rvmc_rv_replay_f64": (_I, [_I64, OrbitSoA, _VP, _VP, _VP]),
+    "rvmc_orbit_scales_f64": (_I, [_I64, OrbitSoA, _VP, _VP, _VP, _VP]),
+    "rvmc_rv_from_vmax_f64": (_I, [_I64, OrbitSoA, _VP, _VP, _VP]),
     "rvmc_rv_replay_f32": (_I, [_I64, OrbitSoA, C.POINTER(PopParams), _VP, _VP, _VP, _VP]),
     "rvmc_mix_pool": (_I, [_U64, _U32, _I64, _D, _VP, _VP, _VP, _VP]),
     "rvmc_sigma1d_pool": (_I, [_U64, _U32, _VP, _I64, _VP, _I, _I, _I, _U64, _I64, _VP, _VP]),
     "rvmc_sigma1d_fused": (_I, [C.POINTER(PopParams), _U64, _VP, _I, _I, _I, _U64, _I64, _VP, _VP, _VP]),
     "rvmc_fused_trace": (_I, [C.POINTER(PopParams), _U64, _VP, _I, _U64, _I64, TraceSoA, _VP]),
-    "rvmc_biascorr_fused": (_I, [C.POINTER(PopParams), _U64, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _I, _F,
+    "rvmc_biascorr_fused": (_I, [C.POINTER(PopParams), _U64, _U64, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _I, _F,
                                  _F, _U64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP]),
-    "rvmc_biascorr_sample": (_I, [C.POINTER(PopParams), _U64, _I, _I, _VP, _VP, _U64, _I64, OrbitSoA, _VP]),
+    "rvmc_biascorr_sample": (_I, [C.POINTER(PopParams), _U64, _I, _I, _VP, _VP, _U64, _I64, _U32, OrbitSoA, _VP]),
+    "rvmc_kepler_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
+    "rvmc_rv_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rvmc_biascorr_replay_f64": (_I, [_I, _I64, _I, _VP, _VP, OrbitSoA, _I64, _VP, _U64, _U64, _I, _VP, _VP, _VP]),
     "rvmc_biascorr_singles": (_I, [_U64, _I, _I, _VP, _VP, _U64, _I64, _VP, _VP]),
     "rvmc_biascorr_detect": (_I, [_I, _I64, _I, _VP, _VP, _VP, _D, _D, _VP, _VP]),

@@ -1,0 +1,544 @@
+"""Drop-in for the reference's `BiasCorr` class (RVMC_bias_corr.py:22-476): multi-epoch
+Delta-RV distributions and binary detection probabilities, computed on the GPU through the C ABI.
+
+Two execution modes, chosen automatically:
+  * FUSED (default): nothing is materialised.  `calculate_radial_velocities()` launches one kernel
+    (rvmc_biascorr_fused) that samples each binary, evaluates its RV at every epoch, adds the
+    measurement noise and writes only Delta-RV (fp32) and the detection flag.  The attribute arrays
+    (`period`, `eccentricity`, ...) and `radial_velocities` are regenerated from the counter-based
+    generator if and when they are read -- same (seed, star, sample) -> same numbers.
+  * REPLAY: as soon as an attribute array has been read or assigned on the host (the user may have
+    edited it, as scripts written for the reference do), or `mass_dist` / `period_dist` were given,
+    the fp64 replay kernel (rvmc_biascorr_replay_f64) evaluates RVMC_bias_corr.py:406-422 on the
+    arrays as they are.
+
+The phase quirk of RVMC_bias_corr.py:357 (mean anomaly = ((2 pi t) mod P)/P) is
+reproduced by default; `physical_phase=True` uses 2 pi frac(t/P) instead.  Additive kwargs:
+`seed`, `device`, `physical_phase`.
+"""
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _abi
+from . import _device as dv
+from .rvmc import _check_powers
+
+_ORBIT = ("primary_mass", "period", "time", "mass_ratio", "eccentricity", "inclination", "orbit_rotation")
+
+
+class BiasCorr(dv.LazyArrays):
+    """Determines the binary-detection bias of a multi-epoch RV campaign by simulating a population
+    of binaries (GPU implementation of RVMC_bias_corr.py:22-476)."""
+
+    _ARRAY_ATTRS = _ORBIT + ("semi_major_axis", "max_orbital_velocity", "delta_rv", "delta_rv_single")
+
+    def __init__(self, t_obs, masses=None, mass_errors=None, number_of_samples=10**4, min_mass=6,
+                 max_mass=20, min_period=10**0.15, max_period=10**3.5, period_pi=-0.5, mass_ratio_kappa=0,
+                 mass_power=-2.35, rv_errors=None, fbin=0.7, period_dist=None, mass_dist=None, min_q=0.1,
+                 max_q=1.0, e_power=-0.5, seed=None, device=None, physical_phase=False):
+        # RVMC_bias_corr.py:160-172
+        self.current_star = 0
+        self.min_q = min_q
+        self.max_q = max_q
+        self.kappa = mass_ratio_kappa
+        self.pi = period_pi
+        self.mass_power = mass_power
+        self.number_of_samples = number_of_samples
+        self.t_obs = t_obs
+        self.number_of_stars = len(t_obs)
+        self.e_power = e_power
+        self.physical_phase = bool(physical_phase)
+        self.seed = dv.fresh_seed() if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._calls = 0
+        self.nonconverged = 0
+        self.counters = None
+        nstars, ns = self.number_of_stars, int(number_of_samples)
+
+        # ---- masses (RVMC_bias_corr.py:175-207) ------------------------------------------------
+        self._mass_mode = 0
+        self._masses = self._mass_errors = None
+        given = 0
+        given_arrays = {}
+        lazy_mass_range = False
+        if masses is not None:
+            if len(masses) != nstars:
+                raise ValueError(f"The number of masses ({len(masses)}) and epoch "
+                                 f"sequences ({len(t_obs)}) are not equal!")
+            self._masses = np.ascontiguousarray(np.reshape(masses, -1), dtype=np.float64)
+            if mass_errors is not None:
+                self._mass_mode = 1
+                self._mass_errors = np.ascontiguousarray(np.reshape(mass_errors, -1), dtype=np.float64)
+                if self._mass_errors.size != nstars:
+                    raise ValueError("operands could not be broadcast together: mass_errors has %d elements, "
+                                     "expected %d" % (self._mass_errors.size, nstars))
+                lazy_mass_range = True           # min/max of the normal draws, computed when asked for
+            else:
+                self._mass_mode = 2
+                self.min_mass = np.min(self._masses) / 2.e30
+                self.max_mass = np.max(self._masses) / 2.e30
+        elif mass_dist is not None:
+            if np.shape(mass_dist) == (len(t_obs), number_of_samples):
+                self.min_mass = np.min(mass_dist) / 2.e30
+                self.max_mass = np.max(mass_dist) / 2.e30
+                given |= 1
+                given_arrays["primary_mass"] = mass_dist
+            else:
+                raise ValueError(f"The shape of mass distributions ({np.shape(mass_dist)})"
+                                 f" not as expected {(len(t_obs), number_of_samples)}.")
+        else:
+            self.min_mass = min_mass
+            self.max_mass = max_mass
+            _check_powers(mass_power=mass_power)
+        self._imf_range = (float(min_mass), float(max_mass))      # what the IMF draw at :207 used
+
+        # ---- periods (:209-223) -----------------------------------------------------------------
+        if period_dist is not None:
+            if np.shape(period_dist) == (len(t_obs), number_of_samples):
+                # the reference overwrites min_mass/max_mass here; kept
+                self.min_mass = np.min(period_dist) / (3600 * 24)
+                self.max_mass = np.max(period_dist) / (3600 * 24)
+                lazy_mass_range = False
+                given |= 2
+                given_arrays["period"] = period_dist
+            else:
+                raise ValueError(f"The shape of period distribution ({np.shape(period_dist)})"
+                                 f" not as expected: {(len(t_obs), number_of_samples)}.")
+        else:
+            self.min_period = min_period
+            self.max_period = max_period
+            _check_powers(period_pi=period_pi)
+
+        # ---- RV errors (:225-235) -----------------------------------------------------------------
+        if rv_errors is None:
+            self.rv_errors = None
+        else:
+            if isinstance(rv_errors, (float, int)):
+                self.rv_errors = rv_errors
+            elif isinstance(rv_errors, (list, np.ndarray)):
+                if len(rv_errors) == nstars:
+                    self.rv_errors = rv_errors
+                else:
+                    raise ValueError(f"The number of radial velocity uncertainties ({len(rv_errors)}) does not match"
+                                     f"the number of stars ({self.number_of_stars}).")
+            # any other type: the reference silently leaves the attribute unset
+        _check_powers(mass_ratio_kappa=mass_ratio_kappa, e_power=e_power)
+
+        self._lazy_init(dv.resolve_device(device))
+        self._given = given
+        self._lazy_mass_range = lazy_mass_range
+        for k, v in given_arrays.items():
+            setattr(self, k, v)                       # host-authoritative -> replay mode
+        self._generated = set()                       # orbit attributes regenerated from the seed so far
+        self._seed0 = self._next_seed()
+        self._rv_seed = None
+        self._rv_cache = None                         # device results of the last RV pass
+        self._rv_user = None                          # user-assigned radial_velocities
+        self.fbin = fbin
+        self.delta_rv_single = None
+        self._set_device("delta_rv", dv.zeros((nstars, ns), "float32", self._device))     # :251
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def _next_seed(self):
+        s = dv.splitmix64((self.seed + self._calls) & 0xFFFFFFFFFFFFFFFF)
+        self._calls += 1
+        return s
+
+    def __getattr__(self, name):
+        d = self.__dict__
+        if "_host" in d:
+            if name in _ORBIT and name not in d["_host"] and name not in d["_dev"]:
+                self._materialize((name,))
+            elif name in ("semi_major_axis", "max_orbital_velocity") and not self._has(name):
+                return None                                               # RVMC_bias_corr.py:246-247
+            elif name in ("min_mass", "max_mass") and d.get("_lazy_mass_range"):
+                pm = self._orbit_on_device(("primary_mass",))["primary_mass"]
+                object.__setattr__(self, "min_mass", float(pm.min().item()) / 2.e30)      # :186-187
+                object.__setattr__(self, "max_mass", float(pm.max().item()) / 2.e30)
+                object.__setattr__(self, "_lazy_mass_range", False)
+                return d[name]
+            elif name == "radial_velocities":
+                return self._radial_velocities_list()
+        return dv.LazyArrays.__getattr__(self, name)
+
+    def __setattr__(self, name, value):
+        if name == "radial_velocities" and "_host" in self.__dict__:
+            object.__setattr__(self, "_rv_user", value)
+            return
+        dv.LazyArrays.__setattr__(self, name, value)
+
+    def _pop(self):
+        has_p = "min_period" in self.__dict__
+        kw = dict(mass_power=float(self.mass_power), period_pi=float(self.pi), min_q=float(self.min_q),
+                  max_q=float(self.max_q), mass_ratio_kappa=float(self.kappa), e_power=float(self.e_power),
+                  fbin=float(self.fbin) if "fbin" in self.__dict__ else 0.7)
+        if self._mass_mode == 0 and not (self._given & 1):
+            kw.update(min_mass=self._imf_range[0], max_mass=self._imf_range[1])
+        if has_p:
+            kw.update(min_period=float(self.min_period), max_period=float(self.max_period))
+        return _abi.PopParams.defaults(**kw)
+
+    def _tables(self):
+        """Device tables of the observing campaign: n_epochs[nstars], t_obs / rv_err [nstars][max_epochs]."""
+        nstars = self.number_of_stars
+        nep = np.array([len(np.ravel(t)) for t in self.t_obs], dtype=np.int32)
+        if nstars and nep.min() < 1:
+            raise ValueError("every star needs at least one observing epoch")
+        max_ep = int(nep.max()) if nstars else 1
+        tob = np.zeros((nstars, max_ep), dtype=np.float64)
+        for i, t in enumerate(self.t_obs):
+            tob[i, :nep[i]] = np.ravel(t)
+        err = None
+        if self.__dict__.get("rv_errors", None) is not None:
+            err = np.zeros((nstars, max_ep), dtype=np.float32)
+            for i in range(nstars):
+                self.current_star = i
+                e = self.check_error_shape(int(nep[i]))
+                err[i, :nep[i]] = np.ravel(e) if isinstance(e, np.ndarray) else e
+        dev = self._device
+        return (nep, max_ep, dv.to_device(nep, "int32", dev), dv.to_device(tob, "float64", dev),
+                None if err is None else dv.to_device(err, "float32", dev))
+
+    def _mass_tables(self):
+        dev = self._device
+        m = None if self._masses is None else dv.to_device(self._masses, "float64", dev)
+        me = None if self._mass_errors is None else dv.to_device(self._mass_errors, "float64", dev)
+        return m, me
+
+    def _generate(self, names):
+        """Regenerates orbit attributes from (seed, star, sample) on the device -> {name: tensor}."""
+        dev = self._device
+        nstars, ns = self.number_of_stars, int(self.number_of_samples)
+        tens = {k: dv.empty((nstars, ns), "float64", dev) for k in names}
+        given = 0
+        if "period" in self._host or "period" in self._dev:
+            # time and eccentricity follow the CURRENT periods (RVMC_bias_corr.py:237,240)
+            tens["period"] = self._on_device("period")
+            given |= 2
+        m, me = self._mass_tables()
+        mode = self._mass_mode
+        out_names = dict(tens)
+        if mode == 2 and "primary_mass" in names:
+            # masses at face value have shape (nstars, 1) in the reference (:190)
+            del out_names["primary_mass"]
+        with dv.DeviceGuard(dev):
+            _abi.check(_abi.lib().rvmc_biascorr_sample(C.byref(self._pop()), self._seed0, nstars, mode, dv.ptr(m),
+                                                       dv.ptr(me), 0, ns, given, dv.soa(**out_names),
+                                                       dv.stream_ptr(dev)))
+        if mode == 2 and "primary_mass" in names:
+            tens["primary_mass"] = dv.to_device(self._masses.reshape(-1, 1), "float64", dev)
+        return {k: tens[k] for k in names}
+
+    def _materialize(self, names):
+        for k, v in self._generate(tuple(names)).items():
+            self._set_device(k, v)
+            self._generated.add(k)
+
+    def _orbit_on_device(self, names=_ORBIT):
+        missing = [k for k in names if not self._has(k)]
+        fresh = self._generate(tuple(missing)) if missing else {}
+        return {k: (fresh[k] if k in fresh else self._on_device(k)) for k in names}
+
+    def _replay_mode(self):
+        """True once any orbit attribute is host-authoritative (read, edited or supplied)."""
+        return any(k in self._host for k in _ORBIT)
+
+    # ---- samplers: fresh draws, as each call of the reference's methods gives (:256-328) ----------
+    def _draw(self, field, size=None, given=0):
+        nstars, ns = self.number_of_stars, int(self.number_of_samples)
+        dev = self._device
+        shape = (nstars, ns) if size is None else (tuple(size) if not np.isscalar(size) else (int(size),))
+        n = int(np.prod(shape))
+        out = dv.empty((n,), "float64", dev)
+        tens = {field: out}
+        pop = self._pop()
+        if given & 2:
+            tens["period"] = self._on_device("period") if self._has("period") else \
+                self._orbit_on_device(("period",))["period"]
+        with dv.DeviceGuard(dev):
+            _abi.check(_abi.lib().rvmc_sample_orbits(C.byref(pop), self._next_seed(), 0, n, given, dv.soa(**tens),
+                                                     None, dv.stream_ptr(dev)))
+        return dv.to_host(out).reshape(shape)
+
+    def sample_powerlaw(self, min_val, max_val, power, size=None):
+        _check_powers(power=power)
+        nstars, ns = self.number_of_stars, int(self.number_of_samples)
+        shape = (nstars, ns) if size is None else (tuple(size) if not np.isscalar(size) else (int(size),))
+        n = int(np.prod(shape))
+        dev = self._device
+        out = dv.empty((n,), "float64", dev)
+        pop = _abi.PopParams.defaults(min_q=float(min_val), max_q=float(max_val), mass_ratio_kappa=float(power))
+        with dv.DeviceGuard(dev):
+            _abi.check(_abi.lib().rvmc_sample_orbits(C.byref(pop), self._next_seed(), 0, n, 0,
+                                                     dv.soa(mass_ratio=out), None, dv.stream_ptr(dev)))
+        return dv.to_host(out).reshape(shape)
+
+    def sample_masses(self):
+        return self.sample_powerlaw(self.min_mass, self.max_mass, self.mass_power) * 2e30
+
+    def sample_inclination(self):
+        return self._draw("inclination")
+
+    def sample_period(self):
+        _check_powers(period_pi=self.pi)
+        return self._draw("period")
+
+    def sample_period_old(self):
+        """RVMC_bias_corr.py:290-293 (unused by the reference itself): uniform in sqrt(log10 P)."""
+        lo, hi = np.log10(self.min_period) ** 0.5, np.log10(self.max_period) ** 0.5
+        u = self.sample_powerlaw(lo, hi, 0.0)        # index 0 == uniform between lo and hi
+        return 10 ** (u ** 2) * 24 * 3600
+
+    def sample_mass_ratio(self):
+        _check_powers(mass_ratio_kappa=self.kappa)
+        return self._draw("mass_ratio")
+
+    def sample_orbit_rotation(self):
+        return self._draw("orbit_rotation")
+
+    def sample_eccentricity(self):
+        _check_powers(e_power=self.e_power)
+        return self._draw("eccentricity", given=2)
+
+    def sample_time(self):
+        return self._draw("time", given=2)
+
+    # ---- per-star building blocks (:330-372) ------------------------------------------------------
+    def calculate_semi_major_axis(self):
+        t = self._orbit_on_device(("mass_ratio", "primary_mass", "period"))
+        n = t["period"].numel()
+        pm = t["primary_mass"].expand_as(t["period"]).contiguous()
+        out = dv.empty(tuple(t["period"].shape), "float64", self._device)
+        with dv.DeviceGuard(self._device):
+            _abi.check(_abi.lib().rvmc_orbit_scales_f64(n, dv.soa(mass_ratio=t["mass_ratio"], primary_mass=pm,
+                                                                  period=t["period"]), None, dv.ptr(out), None,
+                                                        dv.stream_ptr(self._device)))
+        self._set_device("semi_major_axis", out)
+
+    def calculate_max_orbital_velocity(self):
+        if not self._has("semi_major_axis"):
+            raise TypeError("unsupported operand type(s) for *: 'float' and 'NoneType'")     # :345 with a = None
+        t = self._orbit_on_device(("mass_ratio", "primary_mass", "period", "eccentricity"))
+        n = t["period"].numel()
+        pm = t["primary_mass"].expand_as(t["period"]).contiguous()
+        a = self._on_device("semi_major_axis")
+        out = dv.empty(tuple(t["period"].shape), "float64", self._device)
+        with dv.DeviceGuard(self._device):
+            _abi.check(_abi.lib().rvmc_orbit_scales_f64(
+                n, dv.soa(mass_ratio=t["mass_ratio"], primary_mass=pm, period=t["period"],
+                          eccentricity=t["eccentricity"]), dv.ptr(a), None, dv.ptr(out), dv.stream_ptr(self._device)))
+        self._set_device("max_orbital_velocity", out)
+
+    def calculate_eccentric_anomaly(self, time_deltas):
+        """Eccentric anomalies of the current star at the given times (:348-358); `time_deltas` has
+        shape (n_epochs, n_samples)."""
+        i = self.current_star
+        dev = self._device
+        t = self._orbit_on_device(("period", "eccentricity"))
+        td = dv.to_device(np.asarray(time_deltas, dtype=np.float64), "float64", dev)
+        nep, ns = td.shape
+        out = dv.empty((nep, ns), "float64", dev)
+        nonconv = dv.zeros((1,), "int32", dev)
+        with dv.DeviceGuard(dev):
+            _abi.check(_abi.lib().rvmc_kepler_epochs_f64(nep, ns, dv.ptr(td), dv.ptr(t["period"][i].contiguous()),
+                                                         dv.ptr(t["eccentricity"][i].contiguous()),
+                                                         0 if self.physical_phase else 1, dv.ptr(out),
+                                                         dv.ptr(nonconv), dv.stream_ptr(dev)))
+        bad = int(nonconv.item())
+        self.nonconverged += bad
+        if bad:
+            warnings.warn("some failed to converge after 50 iterations (%d orbits)" % bad, RuntimeWarning)
+        return dv.to_host(out)
+
+    def binary_radial_velocity(self, eccentric_anomalies_i):
+        """RVs of the current star for the given eccentric anomalies (:360-372)."""
+        i = self.current_star
+        dev = self._device
+        if not self._has("max_orbital_velocity"):
+            raise TypeError("'NoneType' object is not subscriptable")        # :369 with max_orbital_velocity None
+        t = self._orbit_on_device(("eccentricity", "inclination", "orbit_rotation"))
+        vm = self._on_device("max_orbital_velocity")
+        E = dv.to_device(np.asarray(eccentric_anomalies_i, dtype=np.float64), "float64", dev)
+        nep, ns = E.shape
+        out = dv.empty((nep, ns), "float64", dev)
+        with dv.DeviceGuard(dev):
+            _abi.check(_abi.lib().rvmc_rv_epochs_f64(nep, ns, dv.ptr(E), dv.ptr(vm[i].contiguous()),
+                                                     dv.ptr(t["eccentricity"][i].contiguous()),
+                                                     dv.ptr(t["inclination"][i].contiguous()),
+                                                     dv.ptr(t["orbit_rotation"][i].contiguous()), dv.ptr(out),
+                                                     dv.stream_ptr(dev)))
+        return dv.to_host(out)
+
+    def check_error_shape(self, number_of_epochs):
+        """RVMC_bias_corr.py:374-393."""
+        if isinstance(self.rv_errors, (np.ndarray, list)):
+            if isinstance(self.rv_errors[self.current_star], (np.ndarray, list)):
+                if len(self.rv_errors[self.current_star]) == number_of_epochs:
+                    use_err = np.reshape(self.rv_errors[self.current_star], (-1, 1))
+                else:
+                    raise ValueError(f"The number of radial velocity uncertainties "
+                                     f"({len(self.rv_errors[self.current_star])}) does not match the number of epochs,"
+                                     f"({number_of_epochs})")
+            else:
+                use_err = self.rv_errors[self.current_star]
+        else:
+            use_err = self.rv_errors
+        return use_err
+
+    def generate_rv_errors(self, number_of_epochs, number_of_samples):
+        """Fresh measurement errors for the current star, shape (n_epochs, n_samples) (:395-404)."""
+        use_err = self.check_error_shape(number_of_epochs)
+        err = np.broadcast_to(np.asarray(use_err, dtype=np.float64).reshape(-1), (number_of_epochs,))
+        dev = self._device
+        out = dv.empty((number_of_epochs, number_of_samples), "float64", dev)
+        with dv.DeviceGuard(dev):
+            lib = _abi.lib()
+            for k in range(number_of_epochs):
+                _abi.check(lib.rvmc_normal_f64(self._next_seed(), 0, int(number_of_samples), 7, k, 0.0, float(err[k]),
+                                               0, dv.ptr(out[k]), dv.stream_ptr(dev)))
+        return dv.to_host(out)
+
+    # ---- the hot path (:406-476) ---------------------------------------------------------------------
+    def calculate_radial_velocities(self, delta_RV=20, n_sigma_RV=4):
+        """Radial velocities at every epoch for every star and sample; updates `delta_rv`
+        (RVMC_bias_corr.py:406-422).  The detection flags for (delta_RV, n_sigma_RV) are computed in
+        the same pass and cached for `get_detected_binaries`."""
+        dev = self._device
+        nstars, ns = self.number_of_stars, int(self.number_of_samples)
+        nep, max_ep, d_nep, d_tobs, d_err = self._tables()
+        self._rv_seed = self._next_seed()
+        self._rv_user = None
+        quirk = 0 if self.physical_phase else 1
+        if self._replay_mode():
+            t = self._orbit_on_device()
+            pm = t["primary_mass"]
+            rv = dv.empty((nstars, max_ep, ns), "float64", dev)
+            drv = dv.empty((nstars, ns), "float64", dev)
+            with dv.DeviceGuard(dev):
+                _abi.check(_abi.lib().rvmc_biascorr_replay_f64(
+                    nstars, ns, max_ep, dv.ptr(d_nep), dv.ptr(d_tobs),
+                    dv.soa(**{k: t[k].contiguous() for k in _ORBIT}), int(pm.shape[1]) if pm.dim() == 2 else ns,
+                    dv.ptr(d_err), self._rv_seed, 0, quirk, dv.ptr(rv), dv.ptr(drv), dv.stream_ptr(dev)))
+            self._rv_cache = dict(mode="replay", rv=rv, nep=nep, max_ep=max_ep, d_nep=d_nep, d_err=d_err, det={})
+            self._set_device("delta_rv", drv)
+            # the reference also leaves these two behind (:412-413)
+            self.calculate_semi_major_axis()
+            self.calculate_max_orbital_velocity()
+            return
+        drv = dv.empty((nstars, ns), "float32", dev)
+        det = dv.empty((nstars, ns), "uint8", dev) if d_err is not None else None
+        counters = dv.zeros((4,), "int64", dev)
+        per_star = dv.zeros((max(nstars, 1),), "int32", dev)
+        self._launch_fused(nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, None, counters, per_star)
+        self._rv_cache = dict(mode="fused", nep=nep, max_ep=max_ep, d_nep=d_nep, d_tobs=d_tobs, d_err=d_err,
+                              det={(float(delta_RV), float(n_sigma_RV)): det} if det is not None else {},
+                              counters=counters, per_star=per_star)
+        self._set_device("delta_rv", drv)
+
+    def _launch_fused(self, nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
+                      per_star, first_sample=0, n_samples=None):
+        dev = self._device
+        nstars = self.number_of_stars
+        ns = int(self.number_of_samples) if n_samples is None else int(n_samples)
+        m, me = self._mass_tables()
+        with dv.DeviceGuard(dev):
+            _abi.check(_abi.lib().rvmc_biascorr_fused(
+                C.byref(self._pop()), self._seed0, self._rv_seed, nstars, max_ep, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err),
+                self._mass_mode, dv.ptr(m), dv.ptr(me), 0 if self.physical_phase else 1, float(delta_RV),
+                float(n_sigma_RV), int(first_sample), ns, ns, dv.ptr(drv), dv.ptr(det), dv.ptr(rv_out),
+                dv.ptr(counters), dv.ptr(per_star), dv.stream_ptr(dev)))
+
+    def _radial_velocities_list(self):
+        """`radial_velocities`: list of (n_epochs_i, n_samples) arrays (RVMC_bias_corr.py:250,419-421)."""
+        if self._rv_user is not None:
+            return self._rv_user
+        c = self._rv_cache
+        if c is None:
+            return [[]] * self.number_of_stars
+        if c["mode"] == "replay":
+            rv = dv.to_host(c["rv"])
+        else:
+            if "rv_host" not in c:
+                nstars, ns = self.number_of_stars, int(self.number_of_samples)
+                rvd = dv.empty((nstars, c["max_ep"], ns), "float32", self._device)
+                self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], 20, 4, None, None, rvd,
+                                   None, None)
+                c["rv_host"] = dv.to_host(rvd).astype(np.float64)
+            rv = c["rv_host"]
+        out = [rv[i, :c["nep"][i]] for i in range(self.number_of_stars)]
+        self._rv_user = out          # host copy is authoritative from now on (the user may edit it)
+        return out
+
+    def generate_single_delta_rv(self):
+        """Delta-RV of single stars from measurement noise alone (RVMC_bias_corr.py:424-442)."""
+        needed_singles = int((self.number_of_samples - self.fbin * self.number_of_samples) / self.fbin)
+        nstars = self.number_of_stars
+        dev = self._device
+        if self.rv_errors is not None:
+            nep, max_ep, d_nep, _, d_err = self._tables()
+            out = dv.empty((nstars, needed_singles), "float64", dev)
+            with dv.DeviceGuard(dev):
+                _abi.check(_abi.lib().rvmc_biascorr_singles(self._next_seed(), nstars, max_ep, dv.ptr(d_nep),
+                                                            dv.ptr(d_err), 0, needed_singles, dv.ptr(out),
+                                                            dv.stream_ptr(dev)))
+            self._set_device("delta_rv_single", out)
+        else:
+            self.delta_rv_single = np.zeros((nstars, needed_singles))
+            print("Cannot generate single star radial velocities as there are no uncertainties to work with."
+                  "So all are zero. ")
+
+    def get_all_delta_rv(self):
+        """RVMC_bias_corr.py:444-449."""
+        return np.concatenate([np.asarray(self.delta_rv, dtype=np.float64), self.delta_rv_single], axis=1).ravel()
+
+    def get_detected_binaries(self, delta_RV=20, n_sigma_RV=4):
+        """Bool array (n_stars, n_samples): is each simulated observation set detected as a binary
+        (RVMC_bias_corr.py:451-476)."""
+        nstars, ns = self.number_of_stars, int(self.number_of_samples)
+        c = self._rv_cache
+        if c is None and self._rv_user is None:
+            return np.zeros((nstars, ns), dtype=bool)           # radial_velocities is still [[]]*n: no pairs
+        if self.rv_errors is None:
+            raise TypeError("'NoneType' object is not subscriptable")      # err[v1] at :472
+        dev = self._device
+        key = (float(delta_RV), float(n_sigma_RV))
+        if self._rv_user is not None or c["mode"] == "replay":
+            if self._rv_user is not None:
+                nep, max_ep, d_nep, _, d_err = self._tables()
+                rvh = np.zeros((nstars, max_ep, ns), dtype=np.float64)
+                for i, r in enumerate(self._rv_user):
+                    r = np.asarray(r, dtype=np.float64)
+                    if r.size:
+                        rvh[i, :r.shape[0]] = r
+                        nep[i] = r.shape[0]
+                    else:
+                        nep[i] = 0
+                rv = dv.to_device(rvh, "float64", dev)
+                d_nep = dv.to_device(nep, "int32", dev)
+            else:
+                rv, max_ep, d_nep, d_err = c["rv"], c["max_ep"], c["d_nep"], c["d_err"]
+            det = dv.empty((nstars, ns), "uint8", dev)
+            with dv.DeviceGuard(dev):
+                _abi.check(_abi.lib().rvmc_biascorr_detect(nstars, ns, max_ep, dv.ptr(d_nep), dv.ptr(rv), dv.ptr(d_err),
+                                                           float(delta_RV), float(n_sigma_RV), dv.ptr(det),
+                                                           dv.stream_ptr(dev)))
+            return dv.to_host(det).astype(bool)
+        if key not in c["det"]:
+            det = dv.empty((nstars, ns), "uint8", dev)
+            self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], delta_RV, n_sigma_RV, None,
+                               det, None, None, None)
+            c["det"][key] = det
+        return dv.to_host(c["det"][key]).view(np.bool_)
+
+    def detection_counts(self):
+        """Additive helper: per-star detected counts and the global counters of the last fused pass
+        (binary-epoch RVs, detected, fp64-guard lanes, non-converged lanes) without copying the
+        per-binary arrays to the host."""
+        c = self._rv_cache
+        if c is None or c["mode"] != "fused":
+            raise RuntimeError("no fused radial-velocity pass has been run")
+        cnt = dv.to_host(c["counters"])
+        self.counters = dict(binary_epoch_rvs=int(cnt[0]), detected=int(cnt[1]), guard=int(cnt[2]),
+                             nonconverged=int(cnt[3]))
+        return dv.to_host(c["per_star"])[:self.number_of_stars].astype(np.int64), self.counters

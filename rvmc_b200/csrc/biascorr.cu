@@ -1,0 +1,593 @@
+// K5: multi-epoch Delta-RV and detection probability (BiasCorr), fused, plus the materialised
+// fp64 entries that back the drop-in class's attribute arrays and replay workflow.
+//
+// Reference code replaced (file:line under /root/reference):
+//   BiasCorr.__init__ samplers                      RVMC_bias_corr.py:175-243 (via :256-328)
+//   calculate_semi_major_axis / max_orbital_velocity :330-346
+//   calculate_eccentric_anomaly                      :348-358  (phase quirk Q1 at :357)
+//   binary_radial_velocity                           :360-372
+//   generate_rv_errors                               :395-404
+//   calculate_radial_velocities                      :406-422
+//   generate_single_delta_rv                         :424-442
+//   get_detected_binaries                            :451-476
+//
+// Fused kernel: one thread per binary (star i, sample s); the star is block-uniform so the
+// observing epochs, their errors and the pair thresholds of the significance test sit in shared
+// memory.  Per binary: two Philox blocks -> orbit; the period and the per-epoch phase reduction
+// run in fp64 (2 pi t / P reaches ~2e3 turns: fp32 would lose the phase), everything after the
+// mean anomaly is fp32: closed-form starter + Halley, closed-form true anomaly, RV.  Noise is
+// one Philox block per four epochs.  max/min and the pairwise test are taken in registers; only
+// Delta-RV (4 B) and the detection flag (1 B) per binary reach HBM, and both are optional.
+#include "common.cuh"
+#include "pop_derive.h"
+
+namespace rvmc {
+
+#define BC_THREADS 256
+
+struct BcArgs {
+    PopF32 P32;
+    PopF64 P64;
+    uint64_t seed, noise_seed;
+    int32_t nstars, max_epochs;
+    const int32_t* n_epochs;      // [nstars]
+    const double* t_obs;          // [nstars][max_epochs]  s
+    const float* rv_err;          // [nstars][max_epochs]  km/s, or nullptr
+    int32_t mass_mode;            // 0 IMF, 1 N(masses, mass_errors), 2 masses
+    const double* masses;         // [nstars] kg
+    const double* mass_errors;    // [nstars] kg
+    int32_t quirk_phase;
+    int32_t kepler_iters;
+    float delta_rv_min, n_sigma;
+    uint64_t first_sample;
+    int64_t n_samples, sample_stride;
+    int64_t blocks_per_star;
+    float* delta_rv;              // [nstars][sample_stride]
+    uint8_t* detected;            // [nstars][sample_stride]
+    float* rv_out;                // [nstars][max_epochs][sample_stride]
+    unsigned long long* counters; // [4]: binary-epoch RVs, detected, guard, non-converged
+    uint32_t* det_per_star;       // [nstars]
+};
+
+__device__ __forceinline__ uint64_t bc_item(int star, uint64_t sample) {
+    return ((uint64_t)star << 40) + sample;
+}
+
+// Primary mass of (star, sample) in kg for the three mass modes; `u` is the IMF uniform.
+__device__ __forceinline__ double bc_mass_f64(const PopF64& P, int mode, const double* masses,
+                                              const double* mass_errors, int star, uint64_t seed, uint64_t item,
+                                              double u) {
+    if (mode == 0) return powerlaw_f64(P.mass, u) * RVMC_MSUN_KG;                  // RVMC_bias_corr.py:205-207
+    if (mode == 2) return masses[star];                                            // :190
+    // :183 -- N(masses, mass_errors); one Philox block per pair of samples
+    const u32x4 w = philox_block(seed, item >> 1, RVMC_STREAM_MASS, 0);
+    double z0, z1;
+    box_muller_f64(w.x, w.y, z0, z1);
+    return masses[star] + mass_errors[star] * ((item & 1) ? z1 : z0);
+}
+
+// Noise normals of epochs 4g..4g+3 of one binary.
+__device__ __forceinline__ void bc_noise4_f32(uint64_t seed, uint64_t item, uint32_t stream, int g, float z[4]) {
+    const u32x4 w = philox_block(seed, item, stream, (uint32_t)g);
+    box_muller_f32(w.x, w.y, z[0], z[1]);
+    box_muller_f32(w.z, w.w, z[2], z[3]);
+}
+__device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint32_t stream, int g, double z[4]) {
+    const u32x4 w = philox_block(seed, item, stream, (uint32_t)g);
+    box_muller_f64(w.x, w.y, z[0], z[1]);
+    box_muller_f64(w.z, w.w, z[2], z[3]);
+}
+
+template <int NE>
+__global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
+    __shared__ double A_s[NE];            // 2 pi t_obs (quirk) or t_obs (physical)
+    __shared__ float err_s[NE];
+    __shared__ float thr_s[NE * NE];      // pair thresholds max(delta_RV, n_sigma sqrt(ea^2+eb^2))
+    __shared__ int uniform_s;
+    __shared__ unsigned int c_det, c_guard, c_bad;
+
+    const int star = (int)(blockIdx.x / a.blocks_per_star);
+    const int64_t i = (int64_t)(blockIdx.x - (int64_t)star * a.blocks_per_star) * BC_THREADS + threadIdx.x;
+    const int ne = a.n_epochs[star];
+    const bool noisy = a.rv_err != nullptr;
+
+    if (threadIdx.x < ne) {
+        const double t = a.t_obs[(size_t)star * a.max_epochs + threadIdx.x];
+        A_s[threadIdx.x] = a.quirk_phase ? RVMC_TWO_PI * t : t;
+        err_s[threadIdx.x] = noisy ? a.rv_err[(size_t)star * a.max_epochs + threadIdx.x] : 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        c_det = 0;
+        c_guard = 0;
+        c_bad = 0;
+    }
+    __syncthreads();
+    if (noisy) {
+        for (int p = threadIdx.x; p < ne * ne; p += blockDim.x) {
+            const int x = p / ne, y = p - x * ne;
+            const float ex = err_s[x], ey = err_s[y];
+            thr_s[x * NE + y] = fmaxf(a.delta_rv_min, a.n_sigma * sqrtf(fmaf(ex, ex, ey * ey)));
+        }
+        if (threadIdx.x == 0) {
+            int u = 1;
+            for (int k = 1; k < ne; ++k) u &= (err_s[k] == err_s[0]);
+            uniform_s = u;
+        }
+    }
+    __syncthreads();
+
+    const bool valid = i < a.n_samples;
+    unsigned int my_guard = 0, my_bad = 0;
+    bool det = false;
+    if (valid) {
+        const uint64_t sample = a.first_sample + (uint64_t)i;
+        const uint64_t item = bc_item(star, sample);
+        const u32x4 wa = philox_block(a.seed, item, RVMC_STREAM_ORBIT_A, 0);
+        const u32x4 wb = philox_block(a.seed, item, RVMC_STREAM_ORBIT_B, 0);
+
+        // ---- per-binary quantities --------------------------------------------------------------
+        OrbitF32 o;
+        if (a.mass_mode == 0) {
+            const float p = fmaf(a.P32.mass.b, u01_f32(wa.x), a.P32.mass.a);
+            o.log2m = (a.P32.mass.kind == POW_ONE) ? fast_lg2(a.P32.mass.minv * p)
+                                                   : fmaf(a.P32.mass.inv, fast_lg2(p), a.P32.log2_mass_min);
+        } else {
+            const double m = bc_mass_f64(a.P64, a.mass_mode, a.masses, a.mass_errors, star, a.seed, item, 0.0);
+            o.log2m = fast_lg2((float)(m * (1.0 / RVMC_MSUN_KG)));     // m <= 0 -> NaN like the reference (Q12)
+        }
+        // period in fp64: the phase needs ~1e-10 relative on P
+        const double xd = powerlaw_f64(a.P64.logp, u01_f64(wa.y));
+        const double P = RVMC_DAY_S * exp10(xd);
+        const double invP = 1.0 / P;
+        o.x = (float)xd;
+        const double time = u01_f64(wa.z) * P;                          // RVMC_bias_corr.py:328
+        o.q = powerlaw_f32(a.P32.q, u01_f32(wa.w));
+        {
+            const float ue = u01_f32(wb.x);
+            const bool is_long = P > a.P64.p_mid_s;                     // same compare as the fp64 arrays
+            const float e = powerlaw_f32(is_long ? a.P32.e_long : a.P32.e_mid, ue);
+            o.e = (P > a.P64.p_circ_s) ? e : 0.0f;
+        }
+        o.cosi = u01_f32(wb.y);
+        o.sini = fast_sqrt((1.0f - o.cosi) * (1.0f + o.cosi));
+        o.wturn = u01_f32(wb.z);
+        const float K = semi_amplitude_f32(a.P32, o);
+        float sw, cw;
+        sincos_turn(o.wturn, sw, cw);
+        const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
+        const double tw = a.quirk_phase ? RVMC_TWO_PI * time : time;
+
+        // ---- epochs -----------------------------------------------------------------------------
+        float rvs[NE];
+        float vmax = -INFINITY, vmin = INFINITY;
+        float z[4];
+        auto epoch = [&](int k) {
+            if (noisy && (k & 3) == 0) bc_noise4_f32(a.noise_seed, item, RVMC_STREAM_EPOCH, k >> 2, z);
+            float M;
+            double M64;
+            bool neg = false;
+            const double arg = A_s[k] + tw;
+            if (a.quirk_phase) {
+                // ((2 pi t) mod P) / P in [0,1), used as radians (RVMC_bias_corr.py:357)
+                const double kk = floor(arg * invP);
+                double m = fma(-kk, P, arg);
+                m = (m < 0.0) ? m + P : m;
+                m = (m >= P) ? m - P : m;
+                M64 = m * invP;
+                M = (float)M64;
+            } else {
+                const double ph = arg * invP;
+                const double fr = ph - floor(ph);
+                const double fold = fr - rint(fr);                  // [-0.5, 0.5]
+                neg = fold < 0.0;
+                M64 = RVMC_TWO_PI * fabs(fold);
+                M = (float)M64;
+            }
+            int g, b;
+            const float shape = kepler_shape_f32(M, M64, neg, o.e, rome2, sw, cw, a.kepler_iters,
+                                                 a.P32.guard_amp, g, b);
+            my_guard += g;
+            my_bad += b;
+            float rv = K * shape;
+            if (noisy) rv = fmaf(err_s[k], z[k & 3], rv);
+            rvs[k] = rv;
+            vmax = fmaxf(vmax, rv);
+            vmin = fminf(vmin, rv);
+            if (a.rv_out) a.rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
+        };
+        if constexpr (NE <= 16) {
+            // fully unrolled: rvs[] and z[] live in registers
+#pragma unroll
+            for (int k = 0; k < NE; ++k)
+                if (k < ne) epoch(k);
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < ne; ++k) epoch(k);
+        }
+        // np.max/np.min propagate NaN (mass draw <= 0, Q12); fmaxf/fminf would drop it
+        float drv = vmax - vmin;
+        if (K != K) drv = K;
+        if (a.delta_rv) a.delta_rv[(size_t)star * a.sample_stride + i] = drv;
+
+        // ---- significance test --------------------------------------------------------------------
+        if (noisy) {
+            if (uniform_s) {
+                // equal errors: every pair has the same threshold, so the largest difference decides
+                det = (ne >= 2) && (drv > thr_s[1]);
+            } else if constexpr (NE <= 16) {
+#pragma unroll
+                for (int x = 0; x < NE; ++x)
+#pragma unroll
+                    for (int y = x + 1; y < NE; ++y)
+                        if (y < ne) det = det || (fabsf(rvs[x] - rvs[y]) > thr_s[x * NE + y]);
+            } else {
+                for (int x = 0; x < ne; ++x)
+                    for (int y = x + 1; y < ne; ++y) det = det || (fabsf(rvs[x] - rvs[y]) > thr_s[x * NE + y]);
+            }
+        }
+        if (a.detected) a.detected[(size_t)star * a.sample_stride + i] = det ? 1 : 0;
+    }
+
+    // ---- counters ---------------------------------------------------------------------------------
+    const unsigned int ballot = __ballot_sync(0xffffffffu, det);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&c_det, (unsigned int)__popc(ballot));
+    if (my_guard) atomicAdd(&c_guard, my_guard);
+    if (my_bad) atomicAdd(&c_bad, my_bad);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int64_t first = (int64_t)(blockIdx.x - (int64_t)star * a.blocks_per_star) * BC_THREADS;
+        const int64_t nvalid = min((int64_t)BC_THREADS, a.n_samples - first);
+        if (a.counters) {
+            atomicAdd(a.counters + 0, (unsigned long long)(nvalid * ne));
+            if (c_det) atomicAdd(a.counters + 1, (unsigned long long)c_det);
+            if (c_guard) atomicAdd(a.counters + 2, (unsigned long long)c_guard);
+            if (c_bad) atomicAdd(a.counters + 3, (unsigned long long)c_bad);
+        }
+        if (a.det_per_star && c_det) atomicAdd(a.det_per_star + star, c_det);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// materialised fp64 entries
+// ---------------------------------------------------------------------------------------------
+__global__ void biascorr_sample_kernel(PopF64 P, uint64_t seed, int nstars, int mass_mode,
+                                       const double* __restrict__ masses, const double* __restrict__ mass_errors,
+                                       uint64_t first_sample, int64_t n_samples, uint32_t given,
+                                       rvmc_orbit_soa out) {
+    const int64_t total = (int64_t)nstars * n_samples;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int star = (int)(t / n_samples);
+        const int64_t i = t - (int64_t)star * n_samples;
+        const uint64_t item = bc_item(star, first_sample + (uint64_t)i);
+        const u32x4 wa = philox_block(seed, item, RVMC_STREAM_ORBIT_A, 0);
+        const u32x4 wb = philox_block(seed, item, RVMC_STREAM_ORBIT_B, 0);
+        OrbitF64 o = sample_orbit_f64(P, wa, wb);
+        if (mass_mode != 0) o.primary_mass = bc_mass_f64(P, mass_mode, masses, mass_errors, star, seed, item, 0.0);
+        if (given & RVMC_GIVEN_PERIOD) {
+            o.period = out.period[t];
+            o.time = u01_f64(wa.z) * o.period;
+            o.eccentricity = eccentricity_for_period_f64(P, o.period, u01_f64(wb.x));
+        }
+        if (out.primary_mass && !(given & RVMC_GIVEN_MASS)) out.primary_mass[t] = o.primary_mass;
+        if (out.period && !(given & RVMC_GIVEN_PERIOD)) out.period[t] = o.period;
+        if (out.time) out.time[t] = o.time;
+        if (out.mass_ratio) out.mass_ratio[t] = o.mass_ratio;
+        if (out.eccentricity) out.eccentricity[t] = o.eccentricity;
+        if (out.inclination) out.inclination[t] = o.inclination;
+        if (out.orbit_rotation) out.orbit_rotation[t] = o.orbit_rotation;
+    }
+}
+
+// RVMC_bias_corr.py:406-422 in fp64 on caller-supplied arrays (possibly user-overwritten).
+__global__ void biascorr_replay_f64_kernel(int nstars, int64_t n_samples, int max_epochs,
+                                           const int32_t* __restrict__ n_epochs, const double* __restrict__ t_obs,
+                                           rvmc_orbit_soa in, int64_t mass_cols, const float* __restrict__ rv_err,
+                                           uint64_t seed, uint64_t first_sample, int quirk,
+                                           double* __restrict__ rv_out, double* __restrict__ delta_rv) {
+    const int64_t total = (int64_t)nstars * n_samples;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int star = (int)(t / n_samples);
+        const int64_t i = t - (int64_t)star * n_samples;
+        const double m1 = in.primary_mass[mass_cols == 1 ? star : t];
+        const double P = in.period[t], e = in.eccentricity[t], w = in.orbit_rotation[t];
+        const double K = semi_amplitude_f64(m1, P, in.mass_ratio[t], e, in.inclination[t]);
+        const double time = in.time[t];
+        const int ne = n_epochs[star];
+        const uint64_t item = bc_item(star, first_sample + (uint64_t)i);
+        double vmax = -INFINITY, vmin = INFINITY;
+        bool any_nan = false;
+        double z[4];
+        for (int k = 0; k < ne; ++k) {
+            if (rv_err && (k & 3) == 0) bc_noise4_f64(seed, item, RVMC_STREAM_EPOCH, k >> 2, z);
+            const double tt = t_obs[(size_t)star * max_epochs + k] + time;
+            const double M = mean_anomaly_epoch_f64(tt, P, quirk);
+            double resid;
+            const double E = kepler_f64(M, e, resid);
+            double rv = rv_from_K_f64(K, e, w, E);
+            if (rv_err) rv += (double)rv_err[(size_t)star * max_epochs + k] * z[k & 3];
+            if (rv_out) rv_out[((size_t)star * max_epochs + k) * n_samples + i] = rv;
+            any_nan |= (rv != rv);
+            vmax = fmax(vmax, rv);
+            vmin = fmin(vmin, rv);
+        }
+        if (delta_rv) delta_rv[t] = any_nan ? nan("") : vmax - vmin;
+    }
+}
+
+// calculate_eccentric_anomaly(time_deltas) for one star (RVMC_bias_corr.py:348-358)
+__global__ void kepler_epochs_f64_kernel(int n_epochs, int64_t n_samples, const double* __restrict__ td,
+                                         const double* __restrict__ period, const double* __restrict__ ecc, int quirk,
+                                         double* __restrict__ E_out, uint32_t* __restrict__ nonconverged) {
+    const int64_t total = (int64_t)n_epochs * n_samples;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t bad = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t % n_samples;
+        double resid;
+        E_out[t] = kepler_f64(mean_anomaly_epoch_f64(td[t], period[i], quirk), ecc[i], resid);
+        bad += (fabs(resid) > 1e-9) ? 1u : 0u;
+    }
+    if (nonconverged && bad) atomicAdd(nonconverged, bad);
+}
+
+// binary_radial_velocity(eccentric_anomalies_i) for one star (RVMC_bias_corr.py:360-372)
+__global__ void rv_epochs_f64_kernel(int n_epochs, int64_t n_samples, const double* __restrict__ E,
+                                     const double* __restrict__ vmax, const double* __restrict__ ecc,
+                                     const double* __restrict__ incl, const double* __restrict__ omega,
+                                     double* __restrict__ rv_out) {
+    const int64_t total = (int64_t)n_epochs * n_samples;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t % n_samples;
+        const double e = ecc[i];
+        rv_out[t] = rv_from_K_f64(vmax[i] / (1.0 + e) * sin(incl[i]), e, omega[i], E[t]);
+    }
+}
+
+// generate_single_delta_rv (RVMC_bias_corr.py:424-442)
+__global__ void biascorr_singles_kernel(uint64_t seed, int nstars, int max_epochs,
+                                        const int32_t* __restrict__ n_epochs, const float* __restrict__ rv_err,
+                                        uint64_t first_single, int64_t n_singles, double* __restrict__ out) {
+    const int64_t total = (int64_t)nstars * n_singles;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int star = (int)(t / n_singles);
+        const int64_t i = t - (int64_t)star * n_singles;
+        const uint64_t item = bc_item(star, first_single + (uint64_t)i);
+        const int ne = n_epochs[star];
+        double vmax = -INFINITY, vmin = INFINITY;
+        double z[4];
+        for (int k = 0; k < ne; ++k) {
+            if ((k & 3) == 0) bc_noise4_f64(seed, item, RVMC_STREAM_SINGLE, k >> 2, z);
+            const double rv = (double)rv_err[(size_t)star * max_epochs + k] * z[k & 3];
+            vmax = fmax(vmax, rv);
+            vmin = fmin(vmin, rv);
+        }
+        out[t] = vmax - vmin;
+    }
+}
+
+// get_detected_binaries (RVMC_bias_corr.py:451-476) as written, fp64
+__global__ void biascorr_detect_kernel(int nstars, int64_t n_samples, int max_epochs,
+                                       const int32_t* __restrict__ n_epochs, const double* __restrict__ rv,
+                                       const float* __restrict__ rv_err, double delta_rv_min, double n_sigma,
+                                       uint8_t* __restrict__ detected) {
+    const int64_t total = (int64_t)nstars * n_samples;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int star = (int)(t / n_samples);
+        const int64_t i = t - (int64_t)star * n_samples;
+        const int ne = n_epochs[star];
+        const double* col = rv + (size_t)star * max_epochs * n_samples + i;
+        const float* err = rv_err + (size_t)star * max_epochs;
+        bool det = false;
+        for (int x = 0; x < ne; ++x) {
+            const double vx = col[(size_t)x * n_samples];
+            const double ex = (double)err[x];
+            for (int y = x + 1; y < ne; ++y) {
+                const double d = fabs(vx - col[(size_t)y * n_samples]);
+                const double ey = (double)err[y];
+                det = det || ((d / sqrt(ex * ex + ey * ey) > n_sigma) && (d > delta_rv_min));
+            }
+        }
+        detected[t] = det ? 1 : 0;
+    }
+}
+
+}  // namespace rvmc
+
+using namespace rvmc;
+
+static int bc_check_common(const rvmc_pop_params* p, int nstars, int max_epochs, const int32_t* n_epochs) {
+    RVMC_REQUIRE(p != nullptr, "population parameters are NULL");
+    RVMC_REQUIRE(nstars >= 0 && nstars < (1 << 24), "nstars must be in [0, 2^24)");
+    RVMC_REQUIRE(max_epochs >= 1, "max_epochs must be >= 1");
+    RVMC_REQUIRE(nstars == 0 || n_epochs != nullptr, "n_epochs is required");
+    return RVMC_OK;
+}
+
+extern "C" {
+
+int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int nstars, int max_epochs,
+                        const int32_t* n_epochs, const double* t_obs, const float* rv_err, int mass_mode,
+                        const double* masses, const double* mass_errors, int quirk_phase, float delta_rv_min,
+                        float n_sigma, uint64_t first_sample, int64_t n_samples, int64_t sample_stride,
+                        float* delta_rv, uint8_t* detected, float* rv_out, uint64_t* counters,
+                        uint32_t* det_per_star, void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    int rc = bc_check_common(p, nstars, max_epochs, n_epochs);
+    if (rc) return rc;
+    RVMC_REQUIRE(n_samples >= 0, "number_of_samples must be >= 0");
+    RVMC_REQUIRE(sample_stride >= n_samples, "sample_stride must be >= n_samples");
+    RVMC_REQUIRE(mass_mode >= 0 && mass_mode <= 2, "mass_mode must be 0, 1 or 2");
+    RVMC_REQUIRE(mass_mode == 0 || masses != nullptr, "masses are required for mass_mode %d", mass_mode);
+    RVMC_REQUIRE(mass_mode != 1 || mass_errors != nullptr, "mass_errors are required for mass_mode 1");
+    RVMC_REQUIRE(first_sample + (uint64_t)n_samples <= ((uint64_t)1 << 40), "sample index must stay below 2^40");
+    RVMC_REQUIRE(p->kepler_iters >= 1 && p->kepler_iters <= 8, "kepler_iters must be in [1,8]");
+    if (max_epochs > 64) {
+        set_error("%d epochs per star exceed the 64 the fused kernel is built for", max_epochs);
+        return RVMC_ERR_UNSUPPORTED;
+    }
+    BcArgs a;
+    rc = derive_pop<float>(*p, a.P32);
+    if (!rc) rc = derive_pop<double>(*p, a.P64);
+    if (rc) {
+        set_error("float division by zero");
+        return rc;
+    }
+    if (nstars == 0 || n_samples == 0) return RVMC_OK;
+    RVMC_REQUIRE(t_obs != nullptr, "t_obs is required");
+    a.seed = seed;
+    a.noise_seed = noise_seed;
+    a.nstars = nstars;
+    a.max_epochs = max_epochs;
+    a.n_epochs = n_epochs;
+    a.t_obs = t_obs;
+    a.rv_err = rv_err;
+    a.mass_mode = mass_mode;
+    a.masses = masses;
+    a.mass_errors = mass_errors;
+    a.quirk_phase = quirk_phase;
+    a.kepler_iters = p->kepler_iters;
+    a.delta_rv_min = delta_rv_min;
+    a.n_sigma = n_sigma;
+    a.first_sample = first_sample;
+    a.n_samples = n_samples;
+    a.sample_stride = sample_stride;
+    a.blocks_per_star = (n_samples + BC_THREADS - 1) / BC_THREADS;
+    a.delta_rv = delta_rv;
+    a.detected = detected;
+    a.rv_out = rv_out;
+    a.counters = (unsigned long long*)counters;
+    a.det_per_star = det_per_star;
+    const int64_t blocks = a.blocks_per_star * nstars;
+    if (blocks > 0x7fffffffLL) {
+        set_error("too many blocks in one launch (%lld); shard the samples", (long long)blocks);
+        return RVMC_ERR_UNSUPPORTED;
+    }
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (max_epochs <= 8)
+        biascorr_fused_kernel<8><<<(unsigned int)blocks, BC_THREADS, 0, stream>>>(a);
+    else if (max_epochs <= 16)
+        biascorr_fused_kernel<16><<<(unsigned int)blocks, BC_THREADS, 0, stream>>>(a);
+    else      // 17..64 epochs: same code with run-time loops (rvs[] in local memory)
+        biascorr_fused_kernel<64><<<(unsigned int)blocks, BC_THREADS, 0, stream>>>(a);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+int rvmc_biascorr_sample(const rvmc_pop_params* p, uint64_t seed, int nstars, int mass_mode, const double* masses,
+                         const double* mass_errors, uint64_t first_sample, int64_t n_samples, uint32_t given_mask,
+                         rvmc_orbit_soa out, void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(p != nullptr, "population parameters are NULL");
+    RVMC_REQUIRE(nstars >= 0 && nstars < (1 << 24), "nstars must be in [0, 2^24)");
+    RVMC_REQUIRE(n_samples >= 0, "number_of_samples must be >= 0");
+    RVMC_REQUIRE(mass_mode >= 0 && mass_mode <= 2, "mass_mode must be 0, 1 or 2");
+    RVMC_REQUIRE(mass_mode == 0 || masses != nullptr, "masses are required for mass_mode %d", mass_mode);
+    RVMC_REQUIRE(mass_mode != 1 || mass_errors != nullptr, "mass_errors are required for mass_mode 1");
+    RVMC_REQUIRE(first_sample + (uint64_t)n_samples <= ((uint64_t)1 << 40), "sample index must stay below 2^40");
+    PopF64 P;
+    int rc = derive_pop<double>(*p, P);
+    if (rc) {
+        set_error("float division by zero");
+        return rc;
+    }
+    const int64_t total = (int64_t)nstars * n_samples;
+    if (total == 0) return RVMC_OK;
+    RVMC_REQUIRE(!(given_mask & RVMC_GIVEN_PERIOD) || out.period, "given period is NULL");
+    RVMC_REQUIRE(!(given_mask & (RVMC_GIVEN_TIME | RVMC_GIVEN_ECC)), "time / eccentricity cannot be given here");
+    const int threads = 128;
+    biascorr_sample_kernel<<<grid_stride_blocks(total, threads), threads, 0, (cudaStream_t)cuda_stream>>>(
+        P, seed, nstars, mass_mode, masses, mass_errors, first_sample, n_samples, given_mask, out);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+int rvmc_kepler_epochs_f64(int n_epochs, int64_t n_samples, const double* time_deltas, const double* period_row,
+                           const double* ecc_row, int quirk_phase, double* E_out, uint32_t* nonconverged,
+                           void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(n_epochs >= 0 && n_samples >= 0, "bad shape");
+    const int64_t total = (int64_t)n_epochs * n_samples;
+    if (total == 0) return RVMC_OK;
+    RVMC_REQUIRE(time_deltas && period_row && ecc_row && E_out, "array pointers are required");
+    const int threads = 128;
+    kepler_epochs_f64_kernel<<<grid_stride_blocks(total, threads), threads, 0, (cudaStream_t)cuda_stream>>>(
+        n_epochs, n_samples, time_deltas, period_row, ecc_row, quirk_phase, E_out, nonconverged);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+int rvmc_rv_epochs_f64(int n_epochs, int64_t n_samples, const double* E, const double* vmax_row,
+                       const double* ecc_row, const double* incl_row, const double* omega_row, double* rv_out,
+                       void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(n_epochs >= 0 && n_samples >= 0, "bad shape");
+    const int64_t total = (int64_t)n_epochs * n_samples;
+    if (total == 0) return RVMC_OK;
+    RVMC_REQUIRE(E && vmax_row && ecc_row && incl_row && omega_row && rv_out, "array pointers are required");
+    const int threads = 128;
+    rv_epochs_f64_kernel<<<grid_stride_blocks(total, threads), threads, 0, (cudaStream_t)cuda_stream>>>(
+        n_epochs, n_samples, E, vmax_row, ecc_row, incl_row, omega_row, rv_out);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+int rvmc_biascorr_replay_f64(int nstars, int64_t n_samples, int max_epochs, const int32_t* n_epochs,
+                             const double* t_obs, rvmc_orbit_soa in, int64_t mass_cols, const float* rv_err,
+                             uint64_t seed, uint64_t first_sample, int quirk_phase, double* rv_out,
+                             double* delta_rv, void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(nstars >= 0 && nstars < (1 << 24), "nstars must be in [0, 2^24)");
+    RVMC_REQUIRE(n_samples >= 0, "number_of_samples must be >= 0");
+    RVMC_REQUIRE(max_epochs >= 1, "max_epochs must be >= 1");
+    const int64_t total = (int64_t)nstars * n_samples;
+    if (total == 0) return RVMC_OK;
+    RVMC_REQUIRE(n_epochs && t_obs, "n_epochs and t_obs are required");
+    RVMC_REQUIRE(in.primary_mass && in.period && in.time && in.mass_ratio && in.eccentricity && in.inclination &&
+                     in.orbit_rotation,
+                 "primary_mass, period, time, mass_ratio, eccentricity, inclination and orbit_rotation are required");
+    RVMC_REQUIRE(mass_cols == 1 || mass_cols == n_samples, "primary_mass must have 1 or n_samples columns");
+    const int threads = 128;
+    biascorr_replay_f64_kernel<<<grid_stride_blocks(total, threads), threads, 0, (cudaStream_t)cuda_stream>>>(
+        nstars, n_samples, max_epochs, n_epochs, t_obs, in, mass_cols, rv_err, seed, first_sample, quirk_phase,
+        rv_out, delta_rv);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+int rvmc_biascorr_singles(uint64_t seed, int nstars, int max_epochs, const int32_t* n_epochs, const float* rv_err,
+                          uint64_t first_single, int64_t n_singles, double* delta_out, void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(nstars >= 0 && nstars < (1 << 24), "nstars must be in [0, 2^24)");
+    RVMC_REQUIRE(n_singles >= 0, "n_singles must be >= 0");
+    RVMC_REQUIRE(max_epochs >= 1, "max_epochs must be >= 1");
+    const int64_t total = (int64_t)nstars * n_singles;
+    if (total == 0) return RVMC_OK;
+    RVMC_REQUIRE(n_epochs && rv_err && delta_out, "n_epochs, rv_err and delta_out are required");
+    const int threads = 128;
+    biascorr_singles_kernel<<<grid_stride_blocks(total, threads), threads, 0, (cudaStream_t)cuda_stream>>>(
+        seed, nstars, max_epochs, n_epochs, rv_err, first_single, n_singles, delta_out);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+int rvmc_biascorr_detect(int nstars, int64_t n_samples, int max_epochs, const int32_t* n_epochs, const double* rv,
+                         const float* rv_err, double delta_rv_min, double n_sigma, uint8_t* detected,
+                         void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(nstars >= 0 && n_samples >= 0 && max_epochs >= 1, "bad shape");
+    const int64_t total = (int64_t)nstars * n_samples;
+    if (total == 0) return RVMC_OK;
+    RVMC_REQUIRE(n_epochs && rv && rv_err && detected, "n_epochs, rv, rv_err and detected are required");
+    const int threads = 128;
+    biascorr_detect_kernel<<<grid_stride_blocks(total, threads), threads, 0, (cudaStream_t)cuda_stream>>>(
+        nstars, n_samples, max_epochs, n_epochs, rv, rv_err, delta_rv_min, n_sigma, detected);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+}  // extern "C"

@@ -151,56 +151,60 @@ RVMC_HD float kepler_f32(float M, float e, int iters, float& sE, float& cE, floa
 RVMC_HD void kepler_refine_f64(double M, double e, double& E, double& sE, double& cE) {
 #pragma unroll 1
     for (int it = 0; it < 3; ++it) {
-        sE = sin(E);
-        cE = cos(E);
+        sincos_f64_bounded(E, sE, cE);
         E -= (E - e * sE - M) / (1.0 - e * cE);
     }
-    sE = sin(E);
-    cE = cos(E);
+    sincos_f64_bounded(E, sE, cE);
 }
 
 // RV / K = cos(nu + omega) + e cos(omega) with the true anomaly taken in closed form
 // (cos nu = (cos E - e)/(1 - e cos E), sin nu = sqrt(1-e^2) sin E/(1 - e cos E)); equal to the
-// 2*atan(sqrt((1+e)/(1-e)) tan(E/2)) form of RVMC.py:211-212.
-RVMC_HD float rv_shape_f32(float e, float sE, float cE, float sw, float cw) {
+// 2*atan(sqrt((1+e)/(1-e)) tan(E/2)) form of RVMC.py:211-212.  rome2 = sqrt(1 - e^2).
+RVMC_HD float rv_shape_f32(float e, float rome2, float sE, float cE, float sw, float cw) {
     const float rd = fast_rcp(fmaf(-e, cE, 1.0f));
     const float cnu = (cE - e) * rd;
-    const float snu = fast_sqrt((1.0f - e) * (1.0f + e)) * sE * rd;
+    const float snu = rome2 * sE * rd;
     return fmaf(cnu, cw, fmaf(-snu, sw, e * cw));
 }
 
-// Full single-epoch orbital RV of one sampled orbit [km/s]; `sgn` folds M into [0, pi].
-// n_guard counts lanes that took the fp64 path, n_bad lanes whose residual stayed above 1e-5.
-RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float* K_out, int& guard,
-                           int& bad) {
-    const float K = semi_amplitude_f32(P, o);
-    const float M = 6.283185307179586f * fabsf(o.phase);
+// Kepler solve + shape for a mean anomaly of magnitude M in [0, pi] and sign `neg`
+// (M64 is the same magnitude in double, used by the guard only).  The fp64 guard engages when
+// the amplification of an error in M into the true anomaly, sqrt(1-e^2)/(1-e cos E)^2, exceeds
+// guard_amp: only for e > ~0.9, i.e. never with the reference's hard-coded bounds (RVMC.py:158).
+// `guard` / `bad` report the guard path and a residual above 1e-5 (SciPy's RuntimeWarning).
+RVMC_HD float kepler_shape_f32(float M, double M64, bool neg, float e, float rome2, float sw, float cw,
+                               int iters, float guard_amp, int& guard, int& bad) {
     float sE, cE, resid;
-    const float E = kepler_f32(M, o.e, iters, sE, cE, resid);
-    sE = (o.phase < 0.0f) ? -sE : sE;
-    float sw, cw;
-    sincos_turn(o.wturn, sw, cw);
-    float shape;
-    const float dd = fmaf(-o.e, cE, 1.0f);
-    const float ome2 = (1.0f - o.e) * (1.0f + o.e);
-    // amplification of an error in M into nu: sqrt(1-e^2)/(1-e cos E)^2
-    if (dd * dd * P.guard_amp < fast_sqrt(ome2)) {
+    const float E = kepler_f32(M, e, iters, sE, cE, resid);
+    const float dd = fmaf(-e, cE, 1.0f);
+    if (dd * dd * guard_amp < rome2) {
         double E64 = (double)E, s64, c64;
-        const double e64 = (double)o.e;
-        kepler_refine_f64(RVMC_TWO_PI * fabs((double)o.phase), e64, E64, s64, c64);
-        if (o.phase < 0.0f) s64 = -s64;
+        const double e64 = (double)e;
+        kepler_refine_f64(M64, e64, E64, s64, c64);
+        if (neg) s64 = -s64;
         const double rd = 1.0 / (1.0 - e64 * c64);
         const double cnu = (c64 - e64) * rd;
         const double snu = sqrt((1.0 - e64) * (1.0 + e64)) * s64 * rd;
-        const double w = RVMC_TWO_PI * (double)o.wturn;
-        shape = (float)(cnu * cos(w) - snu * sin(w) + e64 * cos(w));
         guard = 1;
         bad = 0;
-    } else {
-        shape = rv_shape_f32(o.e, sE, cE, sw, cw);
-        guard = 0;
-        bad = (fabsf(resid) > 1e-5f) ? 1 : 0;
+        return (float)(cnu * (double)cw - snu * (double)sw + e64 * (double)cw);
     }
+    guard = 0;
+    bad = (fabsf(resid) > 1e-5f) ? 1 : 0;
+    return rv_shape_f32(e, rome2, neg ? -sE : sE, cE, sw, cw);
+}
+
+// Full single-epoch orbital RV of one sampled orbit [km/s]; the sign of the phase folds M into
+// [0, pi].
+RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float* K_out, int& guard,
+                           int& bad) {
+    const float K = semi_amplitude_f32(P, o);
+    const float aphase = fabsf(o.phase);
+    float sw, cw;
+    sincos_turn(o.wturn, sw, cw);
+    const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
+    const float shape = kepler_shape_f32(6.283185307179586f * aphase, RVMC_TWO_PI * (double)aphase,
+                                         o.phase < 0.0f, o.e, rome2, sw, cw, iters, P.guard_amp, guard, bad);
     if (K_out) *K_out = K;
     return K * shape;
 }
@@ -219,7 +223,17 @@ struct OrbitF64 {
 };
 
 RVMC_HD double powerlaw_f64(const PowerLaw<double>& pl, double u) {
-    return pow(pl.a + pl.b * u, pl.inv) * pl.minv;
+    const double p = pl.a + pl.b * u;
+    // exponents 1 and 2 (kappa = 0, pi = e_power = -0.5: the Sana et al. defaults) need no pow()
+    const double y = (pl.kind == POW_ONE) ? p : (pl.kind == POW_TWO) ? p * p : pow(p, pl.inv);
+    return y * pl.minv;
+}
+
+// RVMC.py:148-161 with one uniform slot per orbit
+RVMC_HD double eccentricity_for_period_f64(const PopF64& P, double period, double ue) {
+    if (period > P.p_mid_s) return powerlaw_f64(P.e_long, ue);
+    if (period > P.p_circ_s) return powerlaw_f64(P.e_mid, ue);
+    return 0.0;
 }
 
 RVMC_HD OrbitF64 sample_orbit_f64(const PopF64& P, const u32x4& wa, const u32x4& wb) {
@@ -228,13 +242,7 @@ RVMC_HD OrbitF64 sample_orbit_f64(const PopF64& P, const u32x4& wa, const u32x4&
     o.period = RVMC_DAY_S * pow(10.0, powerlaw_f64(P.logp, u01_f64(wa.y)));
     o.time = u01_f64(wa.z) * o.period;
     o.mass_ratio = powerlaw_f64(P.q, u01_f64(wa.w));
-    const double ue = u01_f64(wb.x);
-    if (o.period > P.p_mid_s)
-        o.eccentricity = powerlaw_f64(P.e_long, ue);
-    else if (o.period > P.p_circ_s)
-        o.eccentricity = powerlaw_f64(P.e_mid, ue);
-    else
-        o.eccentricity = 0.0;
+    o.eccentricity = eccentricity_for_period_f64(P, o.period, u01_f64(wb.x));
     o.inclination = acos(u01_f64(wb.y));
     o.orbit_rotation = u01_f64(wb.z) * RVMC_TWO_PI;
     return o;
@@ -269,15 +277,25 @@ RVMC_HD double kepler_f64(double M, double e, double& resid) {
 }
 
 // RVMC.py:182-212 evaluated as written (semi-major axis, periastron speed, arctan/tan form).
+RVMC_HD double semi_major_axis_f64(double primary_mass, double period, double q) {
+    return cbrt(RVMC_G_VALUE * (1.0 + q) * primary_mass * period * period / (4.0 * 9.869604401089358));
+}
+RVMC_HD double max_orbital_velocity_f64(double primary_mass, double q, double e, double a) {
+    return q * sqrt(RVMC_G_VALUE * primary_mass * (1.0 + e) / ((1.0 + q) * (1.0 - e) * a)) * 0.001;
+}
+RVMC_HD double semi_amplitude_f64(double primary_mass, double period, double q, double e, double inc) {
+    const double a = semi_major_axis_f64(primary_mass, period, q);
+    return max_orbital_velocity_f64(primary_mass, q, e, a) / (1.0 + e) * sin(inc);
+}
+RVMC_HD double rv_from_K_f64(double K, double e, double omega, double E) {
+    const double nu = 2.0 * atan(sqrt((1.0 + e) / (1.0 - e)) * tan(0.5 * E));
+    return K * (e * cos(omega) + cos(nu + omega));
+}
 RVMC_HD double orbit_rv_f64(double primary_mass, double period, double q, double e, double inc,
                             double omega, double E, double* K_out) {
-    const double a = cbrt(RVMC_G_VALUE * (1.0 + q) * primary_mass * period * period /
-                          (4.0 * 9.869604401089358));
-    const double vmax = q * sqrt(RVMC_G_VALUE * primary_mass * (1.0 + e) / ((1.0 + q) * (1.0 - e) * a)) * 0.001;
-    const double K = vmax / (1.0 + e) * sin(inc);
-    const double nu = 2.0 * atan(sqrt((1.0 + e) / (1.0 - e)) * tan(0.5 * E));
+    const double K = semi_amplitude_f64(primary_mass, period, q, e, inc);
     if (K_out) *K_out = K;
-    return K * (e * cos(omega) + cos(nu + omega));
+    return rv_from_K_f64(K, e, omega, E);
 }
 
 // Multi-epoch mean anomaly.  quirk != 0 reproduces RVMC_bias_corr.py:357, whose operator

@@ -21,14 +21,10 @@ struct u32x4 {
 };
 
 RVMC_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#if defined(__CUDA_ARCH__)
-    lo = a * b;
-    hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * (uint64_t)b;
+    // one 32x32->64 multiply: a single IMAD.WIDE.U32 on sm_100a
+    const uint64_t p = (uint64_t)a * (uint64_t)b;
     lo = (uint32_t)p;
     hi = (uint32_t)(p >> 32);
-#endif
 }
 
 template <int ROUNDS = 10>

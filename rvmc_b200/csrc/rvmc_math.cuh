@@ -108,6 +108,35 @@ RVMC_HD void sincos_rad(float x, float& s, float& c) {
     quadrant_fix((int)k, ss, cc, s, c);
 }
 
+// fp64 sin/cos for |x| up to a few hundred radians (guard path: E in [0, pi]).  fdlibm's
+// __kernel_sin/__kernel_cos minimax polynomials on [-pi/4, pi/4] after a three-constant
+// Cody-Waite reduction; ~1 ulp.  Unlike sin()/cos() it carries no large-argument slow path, so
+// the hot kernels need no stack frame and no call.
+RVMC_HD void sincos_f64_bounded(double x, double& s, double& c) {
+    const double k = rint(x * 0.63661977236758134308);
+    double r = fma(-k, 1.57079632673412561417e+00, x);     // pi/2, first 33 bits
+    r = fma(-k, 6.07710050650619224932e-11, r);            // next 33 bits
+    r = fma(-k, 2.02226624879595063154e-21, r);            // tail
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double ss = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cc = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int q = (int)k;
+    const double a = (q & 1) ? cc : ss;
+    const double b = (q & 1) ? ss : cc;
+    s = (q & 2) ? -a : a;
+    c = ((q + 1) & 2) ? -b : b;
+}
+
 // ---- normals ---------------------------------------------------------------------------------
 // Box-Muller from two Philox words: z0 = r cos(theta), z1 = r sin(theta); replaces
 // np.random.normal (legacy polar method) at every noise site of the reference.

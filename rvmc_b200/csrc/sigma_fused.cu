@@ -1,0 +1,612 @@
+// K1-K4 fused: sample + Kepler + RV + per-cluster dispersion in one pass, and K6 (grid search)
+// built on it.
+//
+// Reference code replaced (file:line under /root/reference):
+//   RVMC.__init__ samplers RVMC.py:79-101, calculate_binary_velocities :214-226,
+//   calculate_radial_velocity :228-236 and subsample :238-273 in the infinite-pool limit
+//   (SURVEY 7.2): every star of a cluster realization is a binary with probability fbin -- a fresh
+//   orbit plus N(0, sigma_dyn) -- else a single N(0, sigma_dyn); plus N(0, err_j);
+//   create_sig1D_distribution findBestDistributions.py:21-32 (ddof = 0 there);
+//   the statistics of get_Pdistr_stats / get_fbinDist_stats :47-60 / :86-99.
+//
+// Kernel structure (one tile of R realizations x S stars per block, T = R*S star slots):
+//   phase A  one thread per PAIR of slots: one Philox block -> two binary/single coins + one
+//            Box-Muller pair; noise goes to v[slot] in shared memory, binary slots are appended to
+//            a shared work queue (warp-aggregated atomics);
+//   phase B  the queue is consumed 32 binaries per warp at a time: orbit sampling, Kepler solve
+//            and RV run on fully populated warps whatever fbin is (no lane idles on a single
+//            star); v[slot] += RV;
+//   phase C  cluster_reduce.cuh: two-pass dispersion per realization by sub-warp groups.
+// Every value is a function of (seed, global slot index) only, so the result does not depend on
+// the tile size, the launch geometry or the GPU the tile ran on.  Per-star values never reach HBM.
+#include <vector>
+
+#include "cluster_reduce.cuh"
+#include "common.cuh"
+#include "pop_derive.h"
+
+namespace rvmc {
+
+struct FusedPoint {
+    PopF32 pop;
+    uint32_t seed_lo, seed_hi;
+    uint32_t coin_thresh;      // binary iff (word >> 8) < coin_thresh ; coin_thresh = round(fbin * 2^24)
+    int32_t kepler_iters;
+};
+
+struct FusedArgs {
+    FusedPoint single;         // the population when points == nullptr (single-population launch)
+    const FusedPoint* points;  // device, one per grid point, or nullptr
+    const float* meas_err;     // device [S]
+    float* sigma_out;          // [n_points][sigma_stride]
+    unsigned long long* counters;   // [4] or nullptr: binary RVs, guard lanes, non-converged lanes
+    uint64_t first_real;
+    int64_t n_real;            // realizations per point
+    int64_t sigma_stride;
+    int32_t S, R, G, tiles_per_point, weighted, ddof;
+};
+
+__device__ __forceinline__ uint64_t seed_of(const FusedPoint& p) {
+    return ((uint64_t)p.seed_hi << 32) | p.seed_lo;
+}
+
+// The slot's noise scale: the two independent normals N(0, sigma_dyn) (RVMC.py:101,224) and
+// N(0, err_j) (RVMC.py:265,271) are drawn as one normal of the summed variance.
+__device__ __forceinline__ float slot_scale(float sigma_dyn, float err) {
+    return sqrtf(fmaf(sigma_dyn, sigma_dyn, err * err));
+}
+
+__global__ void __launch_bounds__(256) sigma1d_fused_kernel(FusedArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.S;
+    const int T = a.R * S;
+    float* v = reinterpret_cast<float*>(smem_raw);               // [T]
+    float* scale = v + T;                                        // [S]
+    float* wts = scale + S;                                      // [S]
+    uint16_t* queue = reinterpret_cast<uint16_t*>(wts + S);      // [T]
+    __shared__ FusedPoint pt;
+    __shared__ int qn;
+    __shared__ float wsum_s;
+    __shared__ unsigned int cnt_guard, cnt_bad;
+
+    const int64_t tile = blockIdx.x;
+    const int64_t point = tile / a.tiles_per_point;
+    const int64_t r0 = (tile - point * a.tiles_per_point) * a.R;
+    const int nr = (int)min((int64_t)a.R, a.n_real - r0);
+    const int nslots = nr * S;
+
+    // stage the point descriptor and the per-star tables
+    if (a.points) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.points + point);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&pt);
+        for (int i = threadIdx.x; i < (int)(sizeof(FusedPoint) / 4); i += blockDim.x) dst[i] = src[i];
+    } else if (threadIdx.x == 0) {
+        pt = a.single;
+    }
+    if (threadIdx.x == 0) {
+        qn = 0;
+        cnt_guard = 0;
+        cnt_bad = 0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        const float e = a.meas_err[j];
+        scale[j] = slot_scale(pt.pop.sigma_dyn, e);
+        wts[j] = 1.0f / (e * e);
+    }
+    __syncthreads();
+    if (a.weighted && threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int j = 0; j < S; ++j) s += wts[j];
+        wsum_s = s;
+    }
+
+    const uint64_t seed = seed_of(pt);
+    const uint64_t slot0 = (a.first_real + (uint64_t)r0) * (uint64_t)S;
+    const uint64_t p_begin = slot0 >> 1;
+    const int npairs = (int)(((slot0 + nslots + 1) >> 1) - p_begin);
+    const float invS = 1.0f / (float)S;
+    const uint32_t thresh = pt.coin_thresh;
+    const int lane = threadIdx.x & 31;
+
+    // ---- phase A: coins + noise ---------------------------------------------------------------
+    const int npairs_pad = (npairs + 31) & ~31;      // whole warps stay in the loop for the ballots
+    for (int pi = threadIdx.x; pi < npairs_pad; pi += blockDim.x) {
+        bool bin0 = false, bin1 = false;
+        int l0 = 0, l1 = 0;
+        if (pi < npairs) {
+            const uint64_t pair = p_begin + pi;
+            const u32x4 w = philox_block(seed, pair, RVMC_STREAM_SLOT, 0);
+            float z0, z1;
+            box_muller_f32(w.z, w.w, z0, z1);
+            const int64_t la = (int64_t)(2 * pair - slot0);
+            l0 = (int)la;
+            l1 = l0 + 1;
+            if (l0 >= 0) {          // l0 < nslots always (pair range)
+                const int r = (int)(((float)l0 + 0.5f) * invS);
+                v[l0] = z0 * scale[l0 - r * S];
+                bin0 = (w.x >> 8) < thresh;
+            }
+            if (l1 < nslots) {
+                const int r = (int)(((float)l1 + 0.5f) * invS);
+                v[l1] = z1 * scale[l1 - r * S];
+                bin1 = (w.y >> 8) < thresh;
+            }
+        }
+        // warp-aggregated append of the binary slots
+        const unsigned m0 = __ballot_sync(0xffffffffu, bin0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, bin1);
+        const int c0 = __popc(m0), c1 = __popc(m1);
+        int base = 0;
+        if (lane == 0 && (c0 + c1)) base = atomicAdd(&qn, c0 + c1);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (bin0) queue[base + __popc(m0 & below)] = (uint16_t)l0;
+        if (bin1) queue[base + c0 + __popc(m1 & below)] = (uint16_t)l1;
+    }
+    __syncthreads();
+
+    // ---- phase B: orbits of the queued binaries -------------------------------------------------
+    const int nq = qn;
+    unsigned int my_guard = 0, my_bad = 0;
+    for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+        const int l = queue[k];
+        const uint64_t slot = slot0 + (uint64_t)l;
+        const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, 0);
+        const u32x4 wb = philox_block(seed, slot, RVMC_STREAM_ORBIT_B, 0);
+        const OrbitF32 o = sample_orbit_f32(pt.pop, wa, wb);
+        int g, b;
+        const float rv = orbit_rv_f32(pt.pop, o, pt.kepler_iters, nullptr, g, b);
+        v[l] += rv;
+        my_guard += g;
+        my_bad += b;
+    }
+    if (my_guard) atomicAdd(&cnt_guard, my_guard);
+    if (my_bad) atomicAdd(&cnt_bad, my_bad);
+    __syncthreads();
+
+    // ---- phase C: dispersion per realization ----------------------------------------------------
+    reduce_tile_sigma<float, float>(v, nr, S, a.G, a.weighted ? wts : nullptr, wsum_s, a.ddof,
+                                    a.sigma_out + point * a.sigma_stride + r0);
+    if (a.counters && threadIdx.x == 0) {
+        atomicAdd(a.counters + 0, (unsigned long long)nq);
+        if (cnt_guard) atomicAdd(a.counters + 1, (unsigned long long)cnt_guard);
+        if (cnt_bad) atomicAdd(a.counters + 2, (unsigned long long)cnt_bad);
+    }
+}
+
+// Per-slot dump of what the fused kernel computes (parity/debug entry): same device functions,
+// same draws; the orbit is evaluated for every slot, `is_binary` says whether K4 would use it.
+__global__ void fused_trace_kernel(FusedPoint pt, const float* __restrict__ meas_err, int S, uint64_t first_slot,
+                                   int64_t n, rvmc_trace_soa out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint64_t seed = seed_of(pt);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t slot = first_slot + (uint64_t)i;
+        const u32x4 ws = philox_block(seed, slot >> 1, RVMC_STREAM_SLOT, 0);
+        const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, 0);
+        const u32x4 wb = philox_block(seed, slot, RVMC_STREAM_ORBIT_B, 0);
+        float z0, z1;
+        box_muller_f32(ws.z, ws.w, z0, z1);
+        const int odd = (int)(slot & 1);
+        const int j = (int)(slot % (uint64_t)S);
+        const float noise = (odd ? z1 : z0) * slot_scale(pt.pop.sigma_dyn, meas_err[j]);
+        const bool is_bin = ((odd ? ws.y : ws.x) >> 8) < pt.coin_thresh;
+        const OrbitF32 o = sample_orbit_f32(pt.pop, wa, wb);
+        int g, b;
+        float K;
+        const float rv = orbit_rv_f32(pt.pop, o, pt.kepler_iters, &K, g, b);
+        if (out.words) {
+            uint32_t* w = out.words + 12 * i;
+            w[0] = wa.x; w[1] = wa.y; w[2] = wa.z; w[3] = wa.w;
+            w[4] = wb.x; w[5] = wb.y; w[6] = wb.z; w[7] = wb.w;
+            w[8] = ws.x; w[9] = ws.y; w[10] = ws.z; w[11] = ws.w;
+        }
+        if (out.log2m) out.log2m[i] = o.log2m;
+        if (out.x) out.x[i] = o.x;
+        if (out.uphase) out.uphase[i] = o.uphase;
+        if (out.q) out.q[i] = o.q;
+        if (out.e) out.e[i] = o.e;
+        if (out.cosi) out.cosi[i] = o.cosi;
+        if (out.wturn) out.wturn[i] = o.wturn;
+        if (out.K) out.K[i] = K;
+        if (out.rv) out.rv[i] = rv;
+        if (out.noise) out.noise[i] = noise;
+        if (out.is_binary) out.is_binary[i] = is_bin ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: per-point statistics of the sigma_1D distribution (findBestDistributions.py:47-60)
+// ---------------------------------------------------------------------------------------------
+// One block per point.  Exact order statistics by a most-significant-digit radix select on the
+// float bit patterns (sigma >= 0, so the unsigned order is the numeric order): four passes of 8
+// bits over the point's sigma array, which the fused kernel has just written and is L2 resident.
+// The ten ranks needed for the 5/16/50/84/95 percentiles (NumPy 'linear' rule: virtual index
+// q/100*(n-1), neighbours floor and floor+1) are selected together; targets that share a prefix
+// share a histogram.  The same passes accumulate the mean (fp64) and the maximum; the `bin`-wide
+// histogram for the mode (first maximal bin, :49-52) is filled in pass 2 once the maximum is known.
+#define STATS_THREADS 512
+#define STATS_TARGETS 10
+#define STATS_MODE_BINS_MAX 8192
+
+struct StatsArgs {
+    const float* sigma;        // [n_points][sigma_stride]
+    int64_t sigma_stride;
+    int64_t n_real;
+    double bin;
+    int32_t hist_bins;         // row length of hist_out
+    rvmc_point_stats* stats_out;
+    uint32_t* hist_out;        // [n_points][hist_bins] or nullptr
+};
+
+__device__ __forceinline__ double block_sum_f64(double x, double* scratch) {
+    // deterministic: warp shuffle tree, then thread 0 adds the warp totals in order
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) scratch[w] = x;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STATS_THREADS / 32; ++i) tot += scratch[i];
+        scratch[0] = tot;
+    }
+    __syncthreads();
+    tot = scratch[0];
+    __syncthreads();
+    return tot;
+}
+
+__global__ void __launch_bounds__(STATS_THREADS) point_stats_kernel(StatsArgs a) {
+    __shared__ unsigned int hist[STATS_TARGETS][256];
+    __shared__ unsigned int mode_hist[STATS_MODE_BINS_MAX];
+    __shared__ double red[STATS_THREADS / 32];
+    __shared__ unsigned int prefix[STATS_TARGETS];      // selected high bits so far, per target
+    __shared__ unsigned int rank[STATS_TARGETS];        // rank still to find inside the prefix
+    __shared__ int group_of[STATS_TARGETS];             // histogram shared by equal prefixes
+    __shared__ unsigned int group_prefix[STATS_TARGETS];
+    __shared__ int n_groups;
+    __shared__ unsigned int max_bits;
+
+    const int64_t n = a.n_real;
+    const float* sig = a.sigma + (size_t)blockIdx.x * a.sigma_stride;
+    rvmc_point_stats* st = a.stats_out + blockIdx.x;
+    const double qs[5] = {5.0, 16.0, 50.0, 84.0, 95.0};
+
+    if (threadIdx.x < STATS_TARGETS) {
+        const int t = threadIdx.x;
+        const double pos = (qs[t >> 1] / 100.0) * (double)(n - 1);
+        int64_t lo = (int64_t)floor(pos);
+        int64_t k = (t & 1) ? min(lo + 1, n - 1) : lo;
+        prefix[t] = 0;
+        rank[t] = (unsigned int)k;
+        group_of[t] = 0;
+    }
+    if (threadIdx.x == 0) {
+        n_groups = 1;
+        group_prefix[0] = 0;
+        max_bits = 0;
+    }
+    for (int i = threadIdx.x; i < STATS_MODE_BINS_MAX; i += blockDim.x) mode_hist[i] = 0;
+
+    double sum = 0.0;
+    unsigned int mx = 0;
+    int nb_mode = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < STATS_TARGETS * 256; i += blockDim.x) (&hist[0][0])[i] = 0;
+        __syncthreads();
+        const int ng = n_groups;
+        const bool do_mode = (pass == 1) && nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX;
+        const double last_edge = (double)nb_mode * a.bin;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const float x = sig[i];
+            const unsigned int bits = __float_as_uint(x);
+            const unsigned int digit = (bits >> shift) & 255u;
+            const unsigned int high = (pass == 0) ? 0u : (bits >> (shift + 8));
+            if (pass == 0) {
+                sum += (double)x;
+                mx = max(mx, bits);
+                // nearly every element shares its top byte: aggregate equal digits inside the warp
+                const unsigned int peers = __match_any_sync(__activemask(), digit);
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[0][digit], __popc(peers));
+            } else {
+                for (int g = 0; g < ng; ++g)
+                    if (high == group_prefix[g]) atomicAdd(&hist[g][digit], 1u);
+            }
+            if (do_mode) {
+                // edges are k*bin (np.arange(0, max+bin, bin)); bin k = [k*bin, (k+1)*bin), the last
+                // bin is closed on the right (np.histogram)
+                const double xd = (double)x;
+                int k = (int)floor(xd / a.bin);
+                if ((double)k * a.bin > xd) --k;
+                else if ((double)(k + 1) * a.bin <= xd) ++k;
+                if (k >= nb_mode && xd <= last_edge) k = nb_mode - 1;
+                if (k >= 0 && k < nb_mode) atomicAdd(&mode_hist[k], 1u);
+            }
+        }
+        if (pass == 0) {
+            atomicMax(&max_bits, mx);
+            sum = block_sum_f64(sum, red);       // contains the barriers
+            const double smax = (double)__uint_as_float(max_bits);
+            // len(np.arange(0, max+bin, bin)) - 1 bins
+            const double nbd = ceil((smax + a.bin) / a.bin) - 1.0;
+            nb_mode = (nbd >= 1.0) ? (nbd < 2.0e9 ? (int)nbd : 2000000000) : 0;   // NaN sigma -> no histogram
+        }
+        __syncthreads();
+        // locate each target's digit: thread t scans its group's 256 counters
+        if (threadIdx.x < STATS_TARGETS) {
+            const int t = threadIdx.x;
+            const unsigned int* h = hist[group_of[t]];
+            unsigned int r = rank[t], d = 0;
+            for (; d < 255; ++d) {
+                const unsigned int c = h[d];
+                if (r < c) break;
+                r -= c;
+            }
+            rank[t] = r;
+            prefix[t] = (prefix[t] << 8) | d;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int ngn = 0;
+            for (int t = 0; t < STATS_TARGETS; ++t) {
+                int g = -1;
+                for (int k = 0; k < ngn; ++k)
+                    if (group_prefix[k] == prefix[t]) g = k;
+                if (g < 0) {
+                    g = ngn++;
+                    group_prefix[g] = prefix[t];
+                }
+                group_of[t] = g;
+            }
+            n_groups = ngn;
+        }
+        __syncthreads();
+    }
+
+    if (threadIdx.x == 0) {
+        double pct[5];
+        for (int k = 0; k < 5; ++k) {
+            // NumPy's _lerp: a + (b-a)*t, evaluated from b when t >= 0.5
+            const double pos = (qs[k] / 100.0) * (double)(n - 1);
+            const double t = pos - floor(pos);
+            const double lo = (double)__uint_as_float(prefix[2 * k]);
+            const double hi = (double)__uint_as_float(prefix[2 * k + 1]);
+            const double diff = hi - lo;
+            pct[k] = (t >= 0.5) ? hi - diff * (1.0 - t) : lo + diff * t;
+        }
+        st->p05 = pct[0];
+        st->p16 = pct[1];
+        st->median = pct[2];
+        st->p84 = pct[3];
+        st->p95 = pct[4];
+        st->mean = sum / (double)n;
+        st->sigma_max = (double)__uint_as_float(max_bits);
+        st->n_hist_bins = (uint32_t)nb_mode;
+        st->n_guard = 0;
+        st->n_nonconverged = 0;
+        st->reserved = 0;
+        if (nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX) {
+            unsigned int best = 0;
+            int arg = 0;
+            for (int k = 0; k < nb_mode; ++k)
+                if (mode_hist[k] > best) {
+                    best = mode_hist[k];
+                    arg = k;
+                }
+            st->mode = (double)arg * a.bin + a.bin / 2.0;
+        } else {
+            // no bin at all (every sigma is 0: the reference's np.max of an empty histogram raises)
+            // or more bins than the kernel's table holds (flagged)
+            st->mode = nan("");
+            st->reserved = nb_mode > STATS_MODE_BINS_MAX ? 1 : 0;
+        }
+    }
+    if (a.hist_out) {
+        uint32_t* ho = a.hist_out + (size_t)blockIdx.x * a.hist_bins;
+        for (int k = threadIdx.x; k < a.hist_bins; k += blockDim.x)
+            ho[k] = (k < nb_mode && k < STATS_MODE_BINS_MAX) ? mode_hist[k] : 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int make_fused_point(const rvmc_pop_params& p, uint64_t seed, FusedPoint* out) {
+    int rc = derive_pop<float>(p, out->pop);
+    if (rc) {
+        set_error("float division by zero");     // RVMC.py:112 with power == -1
+        return rc;
+    }
+    RVMC_REQUIRE(p.fbin >= 0.0 && p.fbin <= 1.0, "fbin must be in [0,1] (got %g)", p.fbin);
+    RVMC_REQUIRE(p.kepler_iters >= 1 && p.kepler_iters <= 8, "kepler_iters must be in [1,8] (got %d)",
+                 p.kepler_iters);
+    RVMC_REQUIRE(p.min_period > 1.0 && p.max_period > p.min_period,
+                 "need 1 d < min_period < max_period (the law is in log10 P, RVMC.py:134)");
+    RVMC_REQUIRE(p.min_mass > 0 && p.max_mass > p.min_mass && p.min_q > 0 && p.max_q > p.min_q,
+                 "need 0 < min < max for the mass and mass-ratio ranges");
+    out->seed_lo = (uint32_t)seed;
+    out->seed_hi = (uint32_t)(seed >> 32);
+    out->coin_thresh = (uint32_t)llrint(p.fbin * 16777216.0);
+    out->kepler_iters = p.kepler_iters;
+    return RVMC_OK;
+}
+
+struct TileShape {
+    int R, G;
+    size_t smem;
+};
+
+static int fused_tile_shape(int S, TileShape* ts) {
+    if (S < 1) {
+        set_error("sample_size must be >= 1 (got %d)", S);
+        return RVMC_ERR_INVALID;
+    }
+    if (S > 8192) {
+        set_error("sample_size %d exceeds the 8192 stars per cluster the fused kernel is built for", S);
+        return RVMC_ERR_UNSUPPORTED;
+    }
+    const int T = 4096;
+    ts->R = S >= T ? 1 : T / S;
+    ts->G = reduce_group_size(S);
+    const size_t slots = (size_t)ts->R * S;
+    ts->smem = slots * sizeof(float) + 2 * (size_t)S * sizeof(float) + slots * sizeof(uint16_t) + 16;
+    return RVMC_OK;
+}
+
+static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, int64_t n_points, const float* meas_err, int S, int weighted,
+                        int ddof, uint64_t first_real, int64_t n_real, float* sigma_out, int64_t sigma_stride,
+                        uint64_t* counters, cudaStream_t stream) {
+    TileShape ts;
+    int rc = fused_tile_shape(S, &ts);
+    if (rc) return rc;
+    if (ts.smem > 48 * 1024)
+        RVMC_CUDA(cudaFuncSetAttribute(sigma1d_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)ts.smem));
+    FusedArgs a;
+    if (single) a.single = *single;
+    a.points = d_points;
+    a.meas_err = meas_err;
+    a.sigma_out = sigma_out;
+    a.counters = (unsigned long long*)counters;
+    a.first_real = first_real;
+    a.n_real = n_real;
+    a.sigma_stride = sigma_stride;
+    a.S = S;
+    a.R = ts.R;
+    a.G = ts.G;
+    a.weighted = weighted;
+    a.ddof = ddof;
+    const int64_t tiles_per_point = (n_real + ts.R - 1) / ts.R;
+    const int64_t total = tiles_per_point * n_points;
+    if (tiles_per_point > 0x7fffffff || total > 0x7fffffff) {
+        set_error("too many tiles in one launch (%lld); split the call", (long long)total);
+        return RVMC_ERR_UNSUPPORTED;
+    }
+    a.tiles_per_point = (int32_t)tiles_per_point;
+    sigma1d_fused_kernel<<<(unsigned int)total, 256, ts.smem, stream>>>(a);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+}  // namespace rvmc
+
+using namespace rvmc;
+
+extern "C" {
+
+int rvmc_sigma1d_fused(const rvmc_pop_params* p, uint64_t seed, const float* meas_err, int sample_size,
+                       int weighted, int ddof, uint64_t first_real, int64_t n_real, float* sigma_out,
+                       uint64_t* counters, void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(p != nullptr, "population parameters are NULL");
+    RVMC_REQUIRE(n_real >= 0, "number_of_samples must be >= 0");
+    RVMC_REQUIRE(ddof == 0 || ddof == 1, "ddof must be 0 or 1");
+    FusedPoint fp;
+    int rc = make_fused_point(*p, seed, &fp);
+    if (rc) return rc;
+    TileShape ts;
+    rc = fused_tile_shape(sample_size, &ts);
+    if (rc) return rc;
+    if (n_real == 0) return RVMC_OK;
+    RVMC_REQUIRE(meas_err && sigma_out, "meas_err and sigma_out are required");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    // one launch covers at most 2^31 tiles
+    const int64_t max_real = (int64_t)ts.R * 0x7fff0000LL;
+    for (int64_t done = 0; done < n_real; done += max_real) {
+        const int64_t chunk = (n_real - done < max_real) ? n_real - done : max_real;
+        rc = launch_fused(&fp, nullptr, 1, meas_err, sample_size, weighted, ddof, first_real + done, chunk,
+                          sigma_out + done, 0, counters, stream);
+        if (rc) return rc;
+    }
+    return RVMC_OK;
+}
+
+int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const float* meas_err, int sample_size,
+                     uint64_t first_slot, int64_t n, rvmc_trace_soa out, void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(p != nullptr, "population parameters are NULL");
+    RVMC_REQUIRE(n >= 0, "n must be >= 0");
+    RVMC_REQUIRE(sample_size >= 1, "sample_size must be >= 1");
+    FusedPoint fp;
+    int rc = make_fused_point(*p, seed, &fp);
+    if (rc) return rc;
+    if (n == 0) return RVMC_OK;
+    RVMC_REQUIRE(meas_err != nullptr, "meas_err is required");
+    const int threads = 128;
+    fused_trace_kernel<<<grid_stride_blocks(n, threads), threads, 0, (cudaStream_t)cuda_stream>>>(
+        fp, meas_err, sample_size, first_slot, n, out);
+    RVMC_LAUNCH_CHECK();
+    return RVMC_OK;
+}
+
+int rvmc_grid_scratch_slots(int device) {
+    (void)device;
+    return 128;
+}
+
+int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* meas_err, int sample_size,
+                  int weighted, int ddof, int64_t n_real, double bin, int hist_bins,
+                  rvmc_point_stats* stats_out, float* sigma_out, uint32_t* hist_out, float* scratch,
+                  uint64_t* counters, void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(n_points >= 0, "n_points must be >= 0");
+    RVMC_REQUIRE(n_real >= 1, "number_of_samples must be >= 1");
+    RVMC_REQUIRE(n_real < ((int64_t)1 << 31), "number_of_samples per grid point must be < 2^31");
+    RVMC_REQUIRE(ddof == 0 || ddof == 1, "ddof must be 0 or 1");
+    RVMC_REQUIRE(bin > 0.0, "bin must be > 0");
+    RVMC_REQUIRE(hist_out == nullptr || hist_bins >= 1, "hist_bins must be >= 1 when hist_out is given");
+    TileShape ts;
+    int rc = fused_tile_shape(sample_size, &ts);
+    if (rc) return rc;
+    if (n_points == 0) return RVMC_OK;
+    RVMC_REQUIRE(points && meas_err && stats_out, "points, meas_err and stats_out are required");
+    RVMC_REQUIRE(sigma_out || scratch, "either sigma_out or scratch must be given");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+    std::vector<FusedPoint> host(n_points);
+    for (int64_t i = 0; i < n_points; ++i) {
+        rc = make_fused_point(points[i].pop, points[i].seed, &host[i]);
+        if (rc) return rc;
+    }
+    // stream-ordered scratch for the descriptors: no library-global state, so concurrent calls on
+    // different streams do not interact
+    void* ws = nullptr;
+    RVMC_CUDA(cudaMallocAsync(&ws, sizeof(FusedPoint) * (size_t)n_points, stream));
+    // the copy from pageable memory has been staged by the time the call returns; `host` may die
+    rc = cuda_status(cudaMemcpyAsync(ws, host.data(), sizeof(FusedPoint) * (size_t)n_points,
+                                     cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(points)");
+    if (rc) {
+        cudaFreeAsync(ws, stream);
+        return rc;
+    }
+    const FusedPoint* d_points = (const FusedPoint*)ws;
+
+    const int64_t tiles_per_point = (n_real + ts.R - 1) / ts.R;
+    int64_t batch = rvmc_grid_scratch_slots(0);
+    if (sigma_out) batch = 0x7fff0000LL / tiles_per_point;       // no scratch limit: as many as one launch takes
+    if (batch < 1) batch = 1;
+    for (int64_t p0 = 0; p0 < n_points; p0 += batch) {
+        const int64_t np = (n_points - p0 < batch) ? n_points - p0 : batch;
+        float* sig = sigma_out ? sigma_out + (size_t)p0 * n_real : scratch;
+        rc = launch_fused(nullptr, d_points + p0, np, meas_err, sample_size, weighted, ddof, 0, n_real, sig, n_real,
+                          counters, stream);
+        if (rc) break;
+        StatsArgs sa;
+        sa.sigma = sig;
+        sa.sigma_stride = n_real;
+        sa.n_real = n_real;
+        sa.bin = bin;
+        sa.hist_bins = hist_bins;
+        sa.stats_out = stats_out + p0;
+        sa.hist_out = hist_out ? hist_out + (size_t)p0 * hist_bins : nullptr;
+        point_stats_kernel<<<(unsigned int)np, STATS_THREADS, 0, stream>>>(sa);
+        rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
+        if (rc) break;
+    }
+    cudaFreeAsync(ws, stream);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,444 @@
+"""Grid-fit entry points of the reference's findBestDistributions.py on the GPU.
+
+The reference file is Python 2, imports a module that is not in its repository and cannot run
+(SURVEY.md top box); what is kept here is its public function names, argument meaning, return
+tuples, statistics rules (findBestDistributions.py:47-60), best-fit rule (:138-158) and on-disk
+formats (:197-201, :276-280, :472-487), restated on top of the B200 kernels:
+
+  * every grid point is one `rvmc_grid_point` (a population + seed); `rvmc_grid_run` evaluates a
+    batch of points with the fused sample+Kepler+RV+dispersion kernel (np.std ddof=0, as at :29-30)
+    and reduces each point's sigma_1D distribution to mode / mean / median / p05 / p16 / p84 / p95 on
+    the device (exact order statistics, NumPy's linear-interpolation percentile rule);
+  * with torch.distributed initialised the points are dealt round-robin to the ranks (one process
+    per GPU, no data-path collective) and only the 80-byte per-point statistics are all-gathered
+    (NCCL over NVLink on GPUs; the same code runs over gloo in the CPU tests).
+
+`create_sig1D_distribution` is the infinite-pool limit of the reference's
+choice-from-a-10^5-star-pool bootstrap (`pool=True` gives the finite-pool version).
+"""
+import ctypes as C
+import os
+import pickle
+
+import numpy as np
+
+from . import _abi
+from . import _device as dv
+
+M17_ERRORS = np.array([0.8, 2.3, 1.0, 1.8, 0.8, 1.0, 1.4, 2.5, 2.0, 0.4, 1.5, 0.6])   # findBestDistributions.py:292
+
+STATS_DTYPE = np.dtype([("mode", "f8"), ("mean", "f8"), ("median", "f8"), ("p05", "f8"), ("p16", "f8"),
+                        ("p84", "f8"), ("p95", "f8"), ("sigma_max", "f8"), ("n_guard", "u4"),
+                        ("n_nonconverged", "u4"), ("n_hist_bins", "u4"), ("reserved", "u4")])
+assert STATS_DTYPE.itemsize == C.sizeof(_abi.PointStats) == 80
+
+
+# ---------------------------------------------------------------------------------------------
+# sharding + gathering (host logic; exercised on CPU with gloo in tests/test_distributed_cpu.py)
+# ---------------------------------------------------------------------------------------------
+def dist_info(group=None):
+    """(rank, world_size) of the current torch.distributed job, (0, 1) when not initialised."""
+    try:
+        import torch.distributed as dist
+    except Exception:          # pragma: no cover
+        return 0, 1
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_indices(n_points, rank, world):
+    """Grid points dealt round-robin: rank r owns r, r+world, ... (cost varies smoothly along the
+    axes, so interleaving balances the ranks)."""
+    return np.arange(rank, n_points, world, dtype=np.int64)
+
+
+def gather_point_stats(local_bytes, n_points, rank, world, group=None):
+    """All-gather of the per-point statistics.  `local_bytes`: uint8 tensor [n_local*80] (CPU for
+    gloo, CUDA for NCCL) holding this rank's rvmc_point_stats in shard order.  Returns a NumPy
+    structured array [n_points] in grid order on every rank."""
+    import torch
+    item = STATS_DTYPE.itemsize
+    if world == 1:
+        return np.frombuffer(local_bytes.detach().cpu().numpy().tobytes(), dtype=STATS_DTYPE).copy()
+    import torch.distributed as dist
+    n_max = (n_points + world - 1) // world
+    pad = torch.zeros(n_max * item, dtype=torch.uint8, device=local_bytes.device)
+    pad[:local_bytes.numel()] = local_bytes
+    out = torch.empty(world * n_max * item, dtype=torch.uint8, device=local_bytes.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    raw = np.frombuffer(out.cpu().numpy().tobytes(), dtype=STATS_DTYPE).reshape(world, n_max)
+    res = np.empty(n_points, dtype=STATS_DTYPE)
+    for r in range(world):
+        idx = shard_indices(n_points, r, world)
+        res[idx] = raw[r, :len(idx)]
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+# core: evaluate a list of grid points
+# ---------------------------------------------------------------------------------------------
+def point_seeds(seed, n_points, common_random_numbers=False):
+    """Per-point seeds.  Distinct by default (independent Monte-Carlo runs, like successive calls of
+    the reference); `common_random_numbers=True` gives every point the same draws, which removes
+    most of the point-to-point noise from the statistic surfaces."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    if common_random_numbers:
+        return [seed] * n_points
+    return [dv.splitmix64((seed + 0x632BE59BD9B4E019 * (i + 1)) & 0xFFFFFFFFFFFFFFFF) for i in range(n_points)]
+
+
+def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**5, bin=0.5, ddof=0,
+               weighted=False, keep_sigma=False, keep_hist=False, hist_bins=2048, device=None, group=None,
+               distributed=True):
+    """Evaluates grid points (list of PopParams + list of seeds) on the GPU(s).
+
+    Returns a dict: 'stats' (structured array [n_points], every rank), 'sigma' (float32
+    [n_points, number_of_samples] or None; local points only are filled when sharded), 'hist'
+    (uint32 [n_points, hist_bins] or None, same remark), 'counters' (binary RVs, guard,
+    non-converged of THIS rank), 'local' (indices this rank computed)."""
+    n_points = len(pops)
+    if len(seeds) != n_points:
+        raise ValueError("need one seed per grid point")
+    err = np.ascontiguousarray(measured_errors, dtype=np.float32)
+    if err.ndim != 1 or err.size != int(sample_size):
+        raise ValueError("measured_errors must have sample_size = %d entries (got shape %s)"
+                         % (int(sample_size), err.shape))
+    for p in pops:
+        if -1.0 in (p.mass_power, p.period_pi, p.mass_ratio_kappa, p.e_power):
+            raise ZeroDivisionError("float division by zero")          # RVMC.py:112
+    rank, world = dist_info(group) if distributed else (0, 1)
+    local = shard_indices(n_points, rank, world)
+    dev = dv.resolve_device(device)
+    t = dv.torch()
+    ns = int(number_of_samples)
+    pts = (_abi.GridPoint * max(len(local), 1))()
+    for k, i in enumerate(local):
+        pts[k].pop = pops[i]
+        pts[k].seed = seeds[i]
+    nl = len(local)
+    stats_d = dv.zeros((max(nl, 1) * STATS_DTYPE.itemsize,), "uint8", dev)
+    errd = dv.to_device(err, "float32", dev)
+    counters = dv.zeros((4,), "int64", dev)
+    sigma_d = dv.empty((nl, ns), "float32", dev) if keep_sigma and nl else None
+    hist_d = dv.zeros((nl, int(hist_bins)), "int32", dev) if keep_hist and nl else None
+    with dv.DeviceGuard(dev):
+        lib = _abi.lib()
+        scratch = None
+        if sigma_d is None and nl:
+            scratch = dv.empty((lib.rvmc_grid_scratch_slots(dev.index), ns), "float32", dev)
+        _abi.check(lib.rvmc_grid_run(pts, nl, dv.ptr(errd), int(sample_size), int(bool(weighted)), int(ddof), ns,
+                                     float(bin), int(hist_bins), dv.ptr(stats_d), dv.ptr(sigma_d), dv.ptr(hist_d),
+                                     dv.ptr(scratch), dv.ptr(counters), dv.stream_ptr(dev)))
+        stats = gather_point_stats(stats_d[:nl * STATS_DTYPE.itemsize], n_points, rank, world, group)
+    out = dict(stats=stats, local=local, counters=dv.to_host(counters), sigma=None, hist=None)
+    if sigma_d is not None:
+        out["sigma"] = dv.to_host(sigma_d)
+    if hist_d is not None:
+        out["hist"] = dv.to_host(hist_d).view(np.uint32)
+    bad = int(stats["reserved"].sum())
+    if bad:
+        raise NotImplementedError("%d grid points have sigma_1D histograms wider than the %d bins the statistics "
+                                  "kernel holds; use a larger `bin`" % (bad, 8192))
+    return out
+
+
+def _pop_for(min_mass, max_mass, fbin, min_period, max_period, sigma_dyn, **extra):
+    return _abi.PopParams.defaults(min_mass=float(min_mass), max_mass=float(max_mass), fbin=float(fbin),
+                                   min_period=float(min_period), max_period=float(max_period),
+                                   sigma_dyn=float(sigma_dyn), **extra)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's entry points
+# ---------------------------------------------------------------------------------------------
+def create_sig1D_distribution(measured_errors=np.zeros(12), number_of_samples=10 ** 5, sample_size=12,
+                              number_of_stars=10 ** 5, min_mass=6, max_mass=20, binary_fraction=0.7, min_period=1.4,
+                              max_period=3500, sigma_dyn=2.0, seed=None, device=None, pool=False):
+    """sigma_1D distribution of `number_of_samples` clusters of `sample_size` stars
+    (findBestDistributions.py:21-32; np.std with ddof=0).  `pool=False`: infinite-pool fused kernel
+    (`number_of_stars` is then irrelevant); `pool=True`: a `number_of_stars` pool is materialised
+    and bootstrapped like the reference does."""
+    from .rvmc import RVMC
+    err = np.broadcast_to(np.asarray(measured_errors, dtype=np.float64), (int(sample_size),))
+    if pool:
+        c = RVMC(number_of_stars=number_of_stars, min_mass=min_mass, max_mass=max_mass, fbin=binary_fraction,
+                 min_period=min_period, max_period=max_period, sigma_dyn=sigma_dyn, seed=seed, device=device)
+        c.calculate_binary_velocities(materialize=False)
+        c.calculate_radial_velocity()
+        dev = c._device
+        poold = c._on_device("radial_velocities")
+        out = dv.empty((int(number_of_samples),), "float64", dev)
+        errd = dv.to_device(err, "float64", dev)
+        with dv.DeviceGuard(dev):
+            _abi.check(_abi.lib().rvmc_sigma1d_pool(c._next_seed(), 0, dv.ptr(poold), poold.numel(), dv.ptr(errd),
+                                                    int(sample_size), 0, 0, 0, int(number_of_samples), dv.ptr(out),
+                                                    dv.stream_ptr(dev)))
+        return dv.to_host(out)
+    dev = dv.resolve_device(device)
+    pop = _pop_for(min_mass, max_mass, binary_fraction, min_period, max_period, sigma_dyn)
+    out = dv.empty((int(number_of_samples),), "float32", dev)
+    errd = dv.to_device(err, "float32", dev)
+    sd = dv.fresh_seed() if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+    with dv.DeviceGuard(dev):
+        _abi.check(_abi.lib().rvmc_sigma1d_fused(C.byref(pop), sd, dv.ptr(errd), int(sample_size), 0, 0, 0,
+                                                 int(number_of_samples), dv.ptr(out), None, dv.stream_ptr(dev)))
+    return dv.to_host(out).astype(np.float64)
+
+
+def _stats_tuple(res, axis_values, bin, number_of_samples, keep_sigma):
+    st = res["stats"]
+    n = len(st)
+    all_sig = [None] * n
+    values, bins = [None] * n, [None] * n
+    for k, i in enumerate(res["local"]):
+        nb = int(st["n_hist_bins"][i])
+        edges = np.arange(0, st["sigma_max"][i] + bin, bin)           # :47
+        bins[i] = edges
+        if res["hist"] is not None:
+            cnt = res["hist"][k, :nb].astype(np.float64)
+            values[i] = cnt / (cnt.sum() * np.diff(edges)) if nb and cnt.sum() else cnt      # density=True
+        if keep_sigma and res["sigma"] is not None:
+            all_sig[i] = res["sigma"][k].astype(np.float64)
+    return (all_sig, list(st["mode"]), list(st["mean"]), list(st["median"]), values, bins, list(st["p05"]),
+            list(st["p16"]), list(st["p84"]), list(st["p95"]), list(axis_values))
+
+
+def get_Pdistr_stats(measured_errors=np.zeros(12), sample_size=12, pmin=1.4, pmax=3300, Npoints=5, bin=0.5,
+                     fbin=0.7, min_mass=6, max_mass=20, number_of_samples=10 ** 5, max_period=3500, sigma_dyn=2.0,
+                     seed=None, device=None, keep_sigma=True, common_random_numbers=False, verbose=False):
+    """Statistics of the sigma_1D distribution for `Npoints` minimum periods log-spaced in
+    [pmin, pmax] (findBestDistributions.py:35-71).  Returns the reference's 11-tuple
+    (allSig1D, mode, mean, median, Allvalues, Allbins, p05, p16, p84, p95, periods)."""
+    periods = np.logspace(np.log10(pmin), np.log10(pmax), Npoints)             # :40
+    sd = dv.fresh_seed() if seed is None else seed
+    pops = [_pop_for(min_mass, max_mass, fbin, p, max_period, sigma_dyn) for p in periods]
+    res = run_points(pops, point_seeds(sd, len(pops), common_random_numbers), _errs(measured_errors, sample_size),
+                     sample_size, number_of_samples, bin=bin, ddof=0, keep_sigma=keep_sigma, keep_hist=True,
+                     device=device)
+    if verbose:
+        for p, s in zip(periods, res["stats"]):
+            print('fbin = %5.2f, Pmin = %5.2f: mode = %5.2f, median = %5.2f, mean = %5.2f, p84 = %5.2f, p16 = %5.2f'
+                  % (fbin, p, s["mode"], s["median"], s["mean"], s["p84"], s["p16"]))
+    return _stats_tuple(res, periods, bin, number_of_samples, keep_sigma)
+
+
+def get_fbinDist_stats(measured_errors=np.zeros(12), sample_size=12, fmin=0., fmax=1., Npoints=100, bin=0.5,
+                       min_period=1.4, min_mass=6, max_mass=20, number_of_samples=10 ** 5, max_period=3500,
+                       sigma_dyn=2.0, seed=None, device=None, keep_sigma=True, common_random_numbers=False,
+                       verbose=False):
+    """Same for `Npoints` binary fractions in [fmin, fmax] (findBestDistributions.py:74-110)."""
+    fbins = np.linspace(fmin, fmax, Npoints)                                   # :78
+    sd = dv.fresh_seed() if seed is None else seed
+    pops = [_pop_for(min_mass, max_mass, f, min_period, max_period, sigma_dyn) for f in fbins]
+    res = run_points(pops, point_seeds(sd, len(pops), common_random_numbers), _errs(measured_errors, sample_size),
+                     sample_size, number_of_samples, bin=bin, ddof=0, keep_sigma=keep_sigma, keep_hist=True,
+                     device=device)
+    if verbose:
+        for f, s in zip(fbins, res["stats"]):
+            print('fbin = %5.2f, Pmin = %5.2f: mode = %5.2f, median = %5.2f, mean = %5.2f, p84 = %5.2f, p16 = %5.2f'
+                  % (f, min_period, s["mode"], s["median"], s["mean"], s["p84"], s["p16"]))
+    return _stats_tuple(res, fbins, bin, number_of_samples, keep_sigma)
+
+
+def _errs(measured_errors, sample_size):
+    return np.broadcast_to(np.asarray(measured_errors, dtype=np.float64), (int(sample_size),))
+
+
+def gaussian(x, mean, amplitude, standard_deviation):
+    return amplitude * np.exp(- ((x - mean) / standard_deviation) ** 2)
+
+
+def find_nearest(array, value):
+    n = [abs(i - value) for i in array]
+    idx = n.index(min(n))
+    return idx, array[idx]
+
+
+def func(x, a, b, c):
+    return a + (b * x) + (c * x * x) + (x * x * x)
+
+
+def best_fit_indices(observed_sigma, mode, median, p05, p16, p84, p95, usemode=False):
+    """findBestDistributions.py:129-158: first strict minimum of |statistic - observed| (initial
+    distance 100, index 0) for the central statistic and the four percentile curves.
+    Returns (index, index05, index16, index84, index95)."""
+    central = mode if usemode else median
+    out = []
+    for curve in (central, p05, p16, p84, p95):
+        diff, index = 100, 0
+        for i, m in enumerate(curve):
+            d = np.abs(m - observed_sigma)
+            if d < diff:
+                diff, index = d, i
+        out.append(index)
+    return tuple(out)
+
+
+def _write_best(path, names, row):
+    """The one-row table astropy's ascii.write produced at findBestDistributions.py:197-201."""
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    with open(path, "w") as f:
+        f.write(" ".join(names) + "\n")
+        f.write(" ".join(repr(float(v)) for v in row) + "\n")
+
+
+def find_best_Pmin(observed_sigma, min_mass, max_mass, sample_size, mode, median, p05, p16, p84, p95, bins, values,
+                   period, usemode=False, outdir="results", write=True, verbose=False):
+    """Best-fitting minimum period and its percentile-crossing error bars (:127-201).  Writes
+    `<outdir>/Pmin_ObsSig_<sigma>_Nstars_<n>_Mass_<a>_<b>.dat` and returns the five periods
+    (best, 0.05, 0.16, 0.84, 0.95)."""
+    index, i05, i16, i84, i95 = best_fit_indices(observed_sigma, mode, median, p05, p16, p84, p95, usemode)
+    row = [period[index], period[i05], period[i16], period[i84], period[i95]]
+    if verbose:
+        print('Pmin = %5.2f' % row[0])
+    if write:
+        _write_best(os.path.join(outdir, 'Pmin_ObsSig_' + str(observed_sigma) + '_Nstars_' + str(sample_size) +
+                                 '_Mass_' + str(min_mass) + '_' + str(max_mass) + '.dat'),
+                    ['best_Pmin', '0.05perc_Pmin', '0.16perc_Pmin', '0.84perc_Pmin', '0.95perc_Pmin'], row)
+    return row
+
+
+def find_best_fbin(observed_sigma, min_mass, max_mass, sample_size, mode, median, p05, p16, p84, p95, bins, values,
+                   fbins, usemode=False, outdir="results", write=True, verbose=False):
+    """Best-fitting binary fraction (:204-282).  Writes `<outdir>/fbin_ObsSig_...dat`; returns
+    `observed_sigma` like the reference.  The five fractions are left in `find_best_fbin.last`."""
+    index, i05, i16, i84, i95 = best_fit_indices(observed_sigma, mode, median, p05, p16, p84, p95, usemode)
+    row = [fbins[index], fbins[i05], fbins[i16], fbins[i84], fbins[i95]]
+    find_best_fbin.last = row
+    if verbose:
+        print('fbin = %5.2f' % row[0])
+    if write:
+        _write_best(os.path.join(outdir, 'fbin_ObsSig_' + str(observed_sigma) + '_Nstars_' + str(sample_size) +
+                                 '_Mass_' + str(min_mass) + '_' + str(max_mass) + '.dat'),
+                    ['best_fbin', '0.05perc_fbin', '0.16perc_fbin', '0.84perc_fbin', '0.95perc_fbin'], row)
+    return observed_sigma
+
+
+def find_Pmin_fbin_individual_clulsters(name_cluster, observed_dispersion, number_stars, min_mass, max_mass,
+                                        number_of_samples=10 ** 5, n_pmin=100, n_fbin=200, seed=None, device=None,
+                                        outdir="results", verbose=False):
+    """Per-cluster best P_min (at fbin 0.7) and best fbin (at P_min 1.4 d) (:285-313).
+    Returns {name: dict(Pmin=[5 values], fbin=[5 values])}."""
+    out = {}
+    sd = dv.fresh_seed() if seed is None else int(seed)
+    for k, (n, sig, ns, m0, m1) in enumerate(zip(name_cluster, observed_dispersion, number_stars, min_mass, max_mass)):
+        RV_errors = M17_ERRORS if n == 'M17' else np.ones(ns) * 1.2          # :291-294
+        t = get_Pdistr_stats(measured_errors=RV_errors, sample_size=ns, pmin=1.4, pmax=3500, Npoints=n_pmin, bin=0.5,
+                             fbin=0.7, min_mass=m0, max_mass=m1, number_of_samples=number_of_samples,
+                             seed=sd + 2 * k, device=device, keep_sigma=False, verbose=verbose)
+        _, mode, mean, median, values, bins, p05, p16, p84, p95, period = t
+        pm = find_best_Pmin(sig, m0, m1, ns, mode, median, p05, p16, p84, p95, bins, values, period, usemode=False,
+                            outdir=outdir, verbose=verbose)
+        t = get_fbinDist_stats(measured_errors=RV_errors, sample_size=ns, fmin=0.00, fmax=1., Npoints=n_fbin, bin=0.5,
+                               min_mass=m0, max_mass=m1, number_of_samples=number_of_samples, seed=sd + 2 * k + 1,
+                               device=device, keep_sigma=False, verbose=verbose)
+        _, mode, mean, median, values, bins, p05, p16, p84, p95, fbins = t
+        find_best_fbin(sig, m0, m1, ns, mode, median, p05, p16, p84, p95, bins, values, fbins, usemode=False,
+                       outdir=outdir, verbose=verbose)
+        out[n] = dict(Pmin=pm, fbin=list(find_best_fbin.last))
+    return out
+
+
+def run_bigGrid(number_stars=20, min_mass=6, max_mass=20, n_fbin=100, n_pmin=100, number_of_samples=10 ** 5,
+                seed=None, device=None, outdir="results", write=True, common_random_numbers=False):
+    """The (f_bin x P_min) grid of findBestDistributions.py:457-489 in ONE sharded launch sequence.
+    Pickles (binary mode) the reference's list of per-f_bin dicts {values, bins, period, fbin, mean,
+    median, mode, p05, p16, p84, p95} and returns it (rank 0 writes the file)."""
+    fbins = np.linspace(0, 1, n_fbin)
+    periods = np.logspace(np.log10(1.4), np.log10(3500), n_pmin)
+    RV_errors = np.ones(number_stars) * 1.2
+    pops = [_pop_for(min_mass, max_mass, f, p, 3500, 2.0) for f in fbins for p in periods]
+    sd = dv.fresh_seed() if seed is None else seed
+    res = run_points(pops, point_seeds(sd, len(pops), common_random_numbers), RV_errors, number_stars,
+                     number_of_samples, bin=0.5, ddof=0, keep_hist=(dist_info()[1] == 1), device=device)
+    st = res["stats"].reshape(n_fbin, n_pmin)
+    l_res = []
+    for a, fbin in enumerate(fbins):
+        result = dict()
+        row = st[a]
+        if res["hist"] is not None:
+            h = res["hist"].reshape(n_fbin, n_pmin, -1)[a]
+            result['values'] = [h[b, :row["n_hist_bins"][b]] / max(1.0, 0.5 * h[b].sum()) for b in range(n_pmin)]
+        else:
+            result['values'] = None
+        result['bins'] = [np.arange(0, row["sigma_max"][b] + 0.5, 0.5) for b in range(n_pmin)]
+        result['period'] = list(periods)
+        result['fbin'] = fbin
+        for key in ('mean', 'median', 'mode', 'p05', 'p16', 'p84', 'p95'):
+            result[key] = list(row[key])
+        l_res.append(result)
+    if write and dist_info()[0] == 0:
+        os.makedirs(outdir, exist_ok=True)
+        output_name = os.path.join(outdir, "grid_Pmin_fbin_Nstars_{}_Mass_{}_{}.pkl".format(number_stars, min_mass,
+                                                                                           max_mass))
+        with open(output_name, "wb") as f:
+            pickle.dump(l_res, f)
+    return l_res
+
+
+def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samples=10 ** 5, observed_sigma=None,
+                base=None, bin=0.5, ddof=0, seed=1, device=None, common_random_numbers=False, group=None,
+                usemode=False):
+    """Generalised grid (BASELINE config 5): `axes` maps population parameter names (any field of
+    rvmc_pop_params: 'period_pi', 'mass_ratio_kappa', 'fbin', 'min_period', ...) to 1-D value
+    arrays; the Cartesian product is evaluated, sharded over the ranks of the current
+    torch.distributed job.  Returns a dict with the per-point statistics reshaped to the grid, the
+    aggregated counters, and -- when `observed_sigma` is given -- the best-fit multi-index
+    (argmin |median - observed|, first minimum in C order, the rule of :138-158)."""
+    names = list(axes.keys())
+    vals = [np.asarray(axes[k], dtype=np.float64) for k in names]
+    shape = tuple(len(v) for v in vals)
+    mesh = np.meshgrid(*vals, indexing="ij")
+    flat = [m.ravel() for m in mesh]
+    base = dict(base or {})
+    pops = [_abi.PopParams.defaults(**dict(base, **{k: float(f[i]) for k, f in zip(names, flat)}))
+            for i in range(int(np.prod(shape)))]
+    res = run_points(pops, point_seeds(seed, len(pops), common_random_numbers), _errs(measured_errors, sample_size),
+                     sample_size, number_of_samples, bin=bin, ddof=ddof, device=device, group=group)
+    out = dict(axes=dict(zip(names, vals)), shape=shape, stats=res["stats"].reshape(shape), counters=res["counters"],
+               n_local=len(res["local"]))
+    if observed_sigma is not None:
+        central = out["stats"]["mode" if usemode else "median"].ravel()
+        d = np.abs(central - observed_sigma)
+        best, idx = 100.0, 0
+        hits = np.nonzero(d < 100)[0]
+        if len(hits):
+            idx = int(np.argmin(d))            # np.argmin returns the first minimum, like the strict `<` loop
+            best = float(d[idx])
+        out["best_index"] = tuple(int(v) for v in np.unravel_index(idx, shape))
+        out["best_params"] = {k: float(v[j]) for k, v, j in zip(names, vals, out["best_index"])}
+        out["best_distance"] = best
+    return out
+
+
+def read_Nstars_massRange(path):
+    """data_RT20/Nstars_massRange.txt -> list of dicts (name, sigma, Nstars, minMass, maxMass, refs);
+    the table plot_grid.py:76 reads with astropy."""
+    rows = []
+    with open(path) as f:
+        header = f.readline().split()
+        for line in f:
+            parts = line.split(None, 5)
+            if len(parts) < 5:
+                continue
+            rows.append(dict(name=parts[0], sigma=float(parts[1]), Nstars=int(parts[2]), minMass=float(parts[3]),
+                             maxMass=float(parts[4]), refs=parts[5].strip() if len(parts) > 5 else ""))
+    assert header[:5] == ['name', 'sigma', 'Nstars', 'minMass', 'maxMass']
+    return rows
+
+
+def read_weighted_RVdisp_vs_age(path):
+    """data_RT20/weighted_RVdisp_vs_age.txt (';'-separated, '#' comments) -> list of dicts
+    (name, age, age_err, sig1D, sig1D_err); the table findBestDistributions.py:338-341 reads."""
+    rows = []
+    with open(path) as f:
+        header = [h.strip() for h in f.readline().split(";")]
+        for line in f:
+            if line.lstrip().startswith("#") or not line.strip():
+                continue
+            parts = [p.strip() for p in line.split(";")]
+            rows.append(dict(name=parts[0], age=float(parts[1]), age_err=float(parts[2]), sig1D=float(parts[3]),
+                             sig1D_err=float(parts[4])))
+    assert header == ['name', 'age', 'age_err', 'sig1D', 'sig1D_err']
+    return rows

@@ -106,6 +106,10 @@ void hc_box_muller(int64_t n, const uint32_t* w1, const uint32_t* w2, float* z0,
     }
 }
 
+void hc_sincos_f64(int64_t n, const double* x, double* s, double* c) {
+    for (int64_t i = 0; i < n; ++i) sincos_f64_bounded(x[i], s[i], c[i]);
+}
+
 void hc_sincos(int64_t n, const float* t, int turn, float* s, float* c) {
     for (int64_t i = 0; i < n; ++i) {
         if (turn) sincos_turn(t[i], s[i], c[i]);

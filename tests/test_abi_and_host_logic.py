@@ -1,0 +1,163 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/rvmc_b200.h
+declares, the ctypes mirror matches the C structs, the host-side API validates like the reference,
+and the product path refuses to run without a GPU (no fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import rvmc_oracle as orc
+from rvmc_b200 import _abi, build, grid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rvmc_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()                        # no-op when up to date; nvcc cross-compiles without a GPU
+    return _abi.lib()
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"RVMC_API\s+[\w\s\*]+?\b(rvmc_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 24
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_abi.SIGNATURES) == declared          # the ctypes table covers the header, no more no less
+    out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    exported = sorted(set(re.findall(r" T (rvmc_\w+)", out)))
+    assert exported == declared                          # -fvisibility=hidden: nothing else leaks
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof/offsetof with ctypes."""
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rvmc_b200.h"\nint main(void){'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rvmc_pop_params), offsetof(rvmc_pop_params, fbin),'
+                   'offsetof(rvmc_pop_params, kepler_iters), sizeof(rvmc_orbit_soa), sizeof(rvmc_trace_soa),'
+                   'sizeof(rvmc_point_stats), sizeof(rvmc_grid_point), offsetof(rvmc_grid_point, seed));return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(_abi.PopParams), _abi.PopParams.fbin.offset, _abi.PopParams.kepler_iters.offset,
+            C.sizeof(_abi.OrbitSoA), C.sizeof(_abi.TraceSoA), C.sizeof(_abi.PointStats), C.sizeof(_abi.GridPoint),
+            _abi.GridPoint.seed.offset]
+    assert got == want
+
+
+def test_defaults_match_reference_constructor(lib):
+    p = _abi.PopParams()
+    lib.rvmc_pop_defaults(C.byref(p))
+    q = _abi.PopParams.defaults()
+    for name, _ in _abi.PopParams._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+    # RVMC.py:28-43 / :155-159
+    assert (p.min_mass, p.max_mass, p.mass_power, p.period_pi, p.mass_ratio_kappa, p.e_power) == (6, 20, -2.35, -0.5, 0, -0.5)
+    assert (p.min_period, p.max_period) == (10 ** 0.15, 10 ** 3.5) and (p.sigma_dyn, p.fbin) == (2.0, 0.7)
+    assert (p.e_min, p.e_max_mid, p.e_max_long, p.p_circ_days, p.p_mid_days) == (1e-5, 0.5, 0.9, 4.0, 6.0)
+    assert lib.rvmc_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    buf = (C.c_uint32 * 4)()
+    rc = lib.rvmc_philox_blocks(1, 0, 1, 0, 0, buf, None)
+    assert rc == _abi.RVMC_ERR_NO_DEVICE and b"no CPU fallback" in lib.rvmc_last_error()
+    with pytest.raises(_abi.RvmcError, match="no CPU fallback"):
+        _abi.check(rc)
+    assert lib.rvmc_device_info(0, None, None, None, None) == _abi.RVMC_ERR_NO_DEVICE
+    from rvmc_b200.rvmc import RVMC
+    from rvmc_b200.bias_corr import BiasCorr
+    with pytest.raises(_abi.RvmcError):
+        RVMC(number_of_stars=10)
+    with pytest.raises(_abi.RvmcError):
+        BiasCorr([[0.0, 1.0]], number_of_samples=4)
+    with pytest.raises(_abi.RvmcError):
+        grid.create_sig1D_distribution(number_of_samples=4)
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under rvmc_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "rvmc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "oracle/" not in text and "oracle." not in text.replace("the oracle.", ""), f
+    code = "import sys; import rvmc_b200, rvmc_b200.rvmc, rvmc_b200.bias_corr, rvmc_b200.grid; " \
+           "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+
+
+def test_argument_errors_come_before_any_device_work():
+    """Validation mirrors the reference and must not need a GPU (RVMC.py:112; RVMC_bias_corr.py:177,201,216,234)."""
+    from rvmc_b200.rvmc import RVMC
+    from rvmc_b200.bias_corr import BiasCorr
+    for kw in (dict(mass_power=-1), dict(period_pi=-1.0), dict(mass_ratio_kappa=-1), dict(e_power=-1)):
+        with pytest.raises(ZeroDivisionError):
+            RVMC(number_of_stars=10, **kw)
+    with pytest.raises(ValueError):
+        RVMC(number_of_stars=10, period_dist=np.ones(3))
+    t = [np.arange(3.0), np.arange(4.0)]
+    with pytest.raises(ValueError, match=r"The number of masses \(1\) and epoch sequences \(2\) are not equal!"):
+        BiasCorr(t, masses=[1e31])
+    with pytest.raises(ValueError, match="not as expected"):
+        BiasCorr(t, mass_dist=np.ones((2, 3)), number_of_samples=4)
+    with pytest.raises(ValueError, match="not as expected"):
+        BiasCorr(t, period_dist=np.ones((3, 4)), number_of_samples=4)
+    with pytest.raises(ValueError, match=r"uncertainties \(3\) does not match"):
+        BiasCorr(t, rv_errors=[1.0, 2.0, 3.0])
+    with pytest.raises(ZeroDivisionError):
+        BiasCorr(t, period_pi=-1)
+    with pytest.raises(ZeroDivisionError):
+        grid.run_points([_abi.PopParams.defaults(e_power=-1.0)], [1], np.ones(12), 12, 10)
+    with pytest.raises(ValueError):
+        grid.run_points([_abi.PopParams.defaults()], [1], np.ones(5), 12, 10)
+
+
+def test_best_fit_rule_and_seeds_and_shards():
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        curves = [list(rng.uniform(0, 60, 30)) for _ in range(6)]
+        obs = rng.uniform(0, 60)
+        assert grid.best_fit_indices(obs, *curves) == orc.best_fit_indices(obs, *curves)
+        assert grid.best_fit_indices(obs, *curves, usemode=True) == orc.best_fit_indices(obs, *curves, usemode=True)
+    far = [500.0] * 4
+    assert grid.best_fit_indices(10.0, far, far, far, far, far, far) == (0, 0, 0, 0, 0)    # nothing within 100
+    s = grid.point_seeds(1, 1000)
+    assert len(set(s)) == 1000 and grid.point_seeds(1, 3, True) == [1, 1, 1] and s == grid.point_seeds(1, 1000)
+    for n, w in ((65536, 8), (10, 4), (3, 8), (0, 2)):
+        parts = [grid.shard_indices(n, r, w) for r in range(w)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert grid.find_nearest([0.1, 0.69, 0.72], 0.70) == (1, 0.69)
+
+
+def test_data_rt20_readers(tmp_path):
+    a = tmp_path / "Nstars_massRange.txt"
+    a.write_text("name sigma Nstars minMass maxMass refs\nIC1805 65.45 8 15 60 \\citet{x}\nM17 5.5 12 6 20 \\citet{paper1}\n")
+    rows = grid.read_Nstars_massRange(str(a))
+    assert rows[1] == dict(name="M17", sigma=5.5, Nstars=12, minMass=6.0, maxMass=20.0, refs="\\citet{paper1}")
+    b = tmp_path / "weighted.txt"
+    b.write_text("name ; age ; age_err ; sig1D ; sig1D_err\nIC1805  ; 2.55 ; 0.95 ; 65.4   ; 3.05\n#G333 ; 1 ; 1 ; 1 ; 1\n"
+                 "R136    ; 1.5 ; 0.5   ; 25.0                ; 5.9\n")
+    rows = grid.read_weighted_RVdisp_vs_age(str(b))
+    assert [r["name"] for r in rows] == ["IC1805", "R136"] and rows[1]["sig1D_err"] == 5.9
+    ref = "/root/reference/data_RT20"
+    if os.path.isdir(ref):          # build container only; the GPU box has no /root/reference
+        assert [r["Nstars"] for r in grid.read_Nstars_massRange(ref + "/Nstars_massRange.txt")] == \
+            [8, 5, 14, 13, 9, 44, 16, 22, 332, 12]
+        assert len(grid.read_weighted_RVdisp_vs_age(ref + "/weighted_RVdisp_vs_age.txt")) == 10

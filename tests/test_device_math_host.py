@@ -177,6 +177,18 @@ def test_box_muller_and_sincos():
     assert np.max(np.abs(c - np.cos(x.astype(np.float64)))) < 2e-7
 
 
+def test_sincos_f64_bounded():
+    lib = load_hostcheck()
+    rng = np.random.RandomState(11)
+    x = np.concatenate([rng.uniform(-10, 10, 100000), rng.uniform(-300, 300, 20000),
+                        np.arange(-8, 9) * np.pi / 4, [0.0]])
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib.hc_sincos_f64(C.c_int64(x.size), x.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p),
+                      c.ctypes.data_as(C.c_void_p))
+    assert np.max(np.abs(s - np.sin(x))) < 5e-16
+    assert np.max(np.abs(c - np.cos(x))) < 5e-16
+
+
 def test_index_minus_one_is_zero_division():
     lib = load_hostcheck()
     p = PopParams.defaults(period_pi=-1.0)
