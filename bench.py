@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Headline benchmark: binary-epoch RVs per second on the multi-epoch detection workload
+(BASELINE.json configs[1]: 10^8 binaries x 6 epochs, Delta-RV > 20 km/s at 4 sigma).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this framework (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, weak scaling
+
+A step = one pass of the hot path (rvmc_biascorr_fused: sample + Kepler + RV at 6 epochs + noise +
+Delta-RV + significance test) over 10^8 binaries per GPU, writing Delta-RV (fp32) and the detection
+flag (u8) for every binary to HBM.  `value` is timed with CUDA events on the launching stream with
+everything resident on the device; `e2e` is the same metric through the drop-in Python class
+(`BiasCorr(...)` -> `calculate_radial_velocities()` -> `get_detected_binaries()`) with host inputs and
+the detection array copied back to host memory inside the timed region.
+
+Only this file's `cpu_baseline` leg and `--impl reference` import `oracle/` (the CPU restatement
+of the reference algorithm); the product path never does.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DAYS6 = np.array([0, 1, 7, 30, 180, 365.0]) * 86400.0
+METRIC = "binary_epoch_rvs_per_sec"
+UNIT = "binary-epoch RV/s"
+
+# algorithmic work per binary-epoch RV on the multi-epoch path
+ALG_FP32_FLOP = 100.0
+ALG_SFU_OPS = 17.0
+ALG_INT_OPS = 55.0
+ALG_FP64_FLOP = 6.0
+ALG_HBM_BYTES = 5.0 / 6.0      # 4 B Delta-RV + 1 B flag per binary of 6 epochs
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_chunk(args):
+    """One bounded sample of the workload on one core: `nstars` stars x `ns` samples x 6 epochs of
+    RVMC_bias_corr.py:175-243,406-422,451-476 (NumPy + SciPy-style vectorised secant)."""
+    seed, nstars, ns = args
+    from oracle import rvmc_oracle as orc
+    rng = np.random.RandomState(seed)
+    shape = (nstars, ns)
+    m1 = orc.masses_from_uniform(rng.random_sample(shape), 6, 20, -2.35)
+    per = orc.period_from_uniform(rng.random_sample(shape), 10 ** 0.15, 10 ** 3.5, -0.5)
+    t = orc.time_from_uniform(rng.random_sample(shape), per)
+    q = orc.mass_ratio_from_uniform(rng.random_sample(shape), 0.1, 1.0, 0)
+    e = np.stack([orc.eccentricity_from_uniform_slotted(per[i], rng.random_sample(ns), -0.5) for i in range(nstars)])
+    inc = orc.inclination_from_uniform(rng.random_sample(shape))
+    om = orc.orbit_rotation_from_uniform(rng.random_sample(shape))
+    ndet = 0
+    for i in range(nstars):
+        rv = orc.multi_epoch_rv(DAYS6, t[i], per[i], e[i], q[i], m1[i], inc[i], om[i])
+        rv = rv + rng.normal(0, 2.0, rv.shape)
+        _ = orc.delta_rv(rv)
+        ndet += int(orc.detected_binaries(rv, 2.0, 20, 4).sum())
+    return nstars * ns * len(DAYS6), ndet
+
+
+def cpu_pass(pool, cores, nstars, ns, seed0):
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_chunk, [(seed0 + c, nstars, ns) for c in range(cores)])
+    dt = time.perf_counter() - t0
+    return sum(r[0] for r in res), dt
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU algorithm on all host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = host_cores()
+    nstars, ns = 2, 50000        # per core and step: 6e5 binary-epoch RVs (~0.6 s at ~1e6 RV/s/core)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for w in range(args.warmup):
+            cpu_pass(pool, cores, nstars, ns, 1000 * w)
+        total, elapsed = 0, 0.0
+        for k in range(args.steps):
+            n, dt = cpu_pass(pool, cores, nstars, ns, 77 + 1000 * k)
+            total += n
+            elapsed += dt
+    value = total / elapsed
+    sample = "%d cores x %d stars x %d samples x 6 epochs per step (oracle port: NumPy + SciPy-style secant)" % (
+        cores, nstars, ns)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus, nstars=100, ns=10 ** 6):
+    return {"workload": "BiasCorr multi-epoch detection (BASELINE configs[1]): %d stars x %d samples = %.0e binaries "
+                        "per GPU x 6 epochs [0,1,7,30,180,365] d, IMF masses 6-20, Sana+2012 defaults, rv_errors 2.0 "
+                        "km/s, Delta-RV > 20 km/s at 4 sigma" % (nstars, ns, nstars * ns),
+            "binaries_per_gpu": nstars * ns, "epochs": 6, "parallelism": "dp%d (samples sharded, no collective)" % n_gpus,
+            "l2": "inputs are < 8 KB of tables; outputs (%.0f MB/step) exceed the 126 MB L2" % (nstars * ns * 5 / 1e6)}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as exc:       # pragma: no cover
+            self.err = repr(exc)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:          # pragma: no cover
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def run_gpu_arm(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from rvmc_b200 import _abi
+    from rvmc_b200 import _device as dv
+    from rvmc_b200.bias_corr import BiasCorr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _abi.lib()
+    p = _abi.PopParams.defaults()
+    nstars, ns = args.stars, args.samples
+    first_sample = rank * ns                 # ranks take disjoint sample ranges of the same stars
+    seed, noise_seed = 1234, 4321
+    st = dv.stream_ptr(dev)
+
+    d_nep = dv.to_device(np.full(nstars, 6, np.int32), "int32", dev)
+    d_tobs = dv.to_device(np.tile(DAYS6, (nstars, 1)), "float64", dev)
+    d_err = dv.to_device(np.full((nstars, 6), 2.0, np.float32), "float32", dev)
+    drv = dv.empty((nstars, ns), "float32", dev)
+    det = dv.empty((nstars, ns), "uint8", dev)
+    cnt = dv.zeros((4,), "int64", dev)
+
+    def step():
+        _abi.check(lib.rvmc_biascorr_fused(C.byref(p), seed, noise_seed, nstars, 6, dv.ptr(d_nep), dv.ptr(d_tobs),
+                                           dv.ptr(d_err), 0, None, None, 1, 20.0, 4.0, first_sample, ns, ns,
+                                           dv.ptr(drv), dv.ptr(det), None, dv.ptr(cnt), None, st))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    cnt.zero_()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    counters = dv.to_host(cnt)
+    units_per_step = nstars * ns * 6
+    assert int(counters[0]) == units_per_step * args.steps, "kernel did not process the whole workload"
+    assert int(counters[3]) == 0, "non-converged Kepler lanes"
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * units_per_step * args.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e: the drop-in class with host inputs and the detection array back on the host ----------
+    t_obs_host = [DAYS6.copy() for _ in range(nstars)]
+    h2d = nstars * 6 * 8 + nstars * 6 * 4 + nstars * 4
+    d2h = nstars * ns
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step(k):
+        bc = BiasCorr(t_obs_host, number_of_samples=ns, rv_errors=2.0, seed=1000 + k + 7919 * rank, device=dev)
+        bc.calculate_radial_velocities(delta_RV=20, n_sigma_RV=4)
+        d = bc.get_detected_binaries(delta_RV=20, n_sigma_RV=4)
+        return d
+
+    for k in range(2):
+        d = e2e_step(-1 - k)
+    frac = float(d.mean())
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        d = e2e_step(k)
+        assert d.shape == (nstars, ns) and d.dtype == np.bool_
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * units_per_step * e2e_steps / float(t.item())
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        launch_ms = float(np.mean(per_launch_ms))
+        rv_per_s_kernel = units_per_step / (launch_ms * 1e-3)
+        pipes = {}
+        if not args.no_pipe_peaks:
+            for kind, name in ((0, "ffma"), (1, "mufu"), (2, "imad_wide"), (3, "dfma"), (4, "issue_mix")):
+                ops, ms = C.c_double(), C.c_double()
+                _abi.check(lib.rvmc_pipe_peak(kind, 2000, C.byref(ops), C.byref(ms)))
+                pipes[name] = ops.value
+        roof = {"bound": "fp32", "achieved": rv_per_s_kernel * ALG_FP32_FLOP / 1e12, "unit": "TFLOP/s", "peak": None,
+                "frac": None, "traffic": args.traffic_bytes,
+                "kernel": "rvmc::biascorr_fused_kernel<8>", "launch_ms": launch_ms,
+                "algorithmic_per_unit": {"fp32_flop": ALG_FP32_FLOP, "sfu_ops": ALG_SFU_OPS, "int_ops": ALG_INT_OPS,
+                                         "fp64_flop": ALG_FP64_FLOP, "hbm_bytes": ALG_HBM_BYTES},
+                "hbm": {"achieved_gbs": rv_per_s_kernel * ALG_HBM_BYTES / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                        "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback",
+                        "frac": rv_per_s_kernel * ALG_HBM_BYTES / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
+        if pipes:
+            fp32_peak = 2.0 * pipes["ffma"] / 1e12
+            fr = {"fp32": roof["achieved"] / fp32_peak,
+                  "sfu": rv_per_s_kernel * ALG_SFU_OPS / pipes["mufu"],
+                  "fp64": rv_per_s_kernel * ALG_FP64_FLOP / (2.0 * pipes["dfma"]),
+                  "int_mul": rv_per_s_kernel * ALG_INT_OPS / pipes["imad_wide"]}
+            bound = max(fr, key=fr.get)
+            roof.update({"peak": fp32_peak, "frac": fr["fp32"], "pipe_fracs": fr, "binding_pipe": bound,
+                         "peak_source": "measured live by rvmc_pipe_peak (FFMA microbenchmark, this device, these "
+                                        "clocks); MEASURED_PEAKS.json has no FP32/SFU figure",
+                         "pipe_peaks_lane_ops_per_s": pipes})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 period/phase reduction)",
+                "data": "synthetic", "config": workload_config(world, nstars, ns), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "api": "BiasCorr(...).calculate_radial_velocities(); get_detected_binaries()",
+                        "detected_fraction": frac},
+                "gpu_launches": args.steps, "roofline": roof,
+                "counters": {"binary_epoch_rvs": int(counters[0]), "detected": int(counters[1]),
+                             "fp64_guard_lanes": int(counters[2]), "nonconverged": int(counters[3])}}
+        if world == 1 and not args.no_cpu_baseline:
+            import multiprocessing as mp
+            cores = host_cores()
+            with mp.get_context("fork").Pool(cores) as pool:
+                cpu_pass(pool, cores, 1, 20000, 5)                  # warm-up (imports, page faults)
+                n, dt = 0, 0.0
+                for k in range(4):
+                    a, b = cpu_pass(pool, cores, 2, 50000, 11 + k)
+                    n += a
+                    dt += b
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "4 passes of %d cores x 2 stars x 50000 samples x 6 epochs (oracle port of "
+                                              "RVMC_bias_corr.py: NumPy + SciPy-style vectorised secant)" % cores}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--stars", type=int, default=100)
+    ap.add_argument("--samples", type=int, default=10 ** 6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipe-peaks", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -67,7 +67,18 @@ def to_device(array, dtype, device):
 
 
 def to_host(tensor):
-    return tensor.detach().cpu().numpy()
+    """Device tensor -> NumPy array.  Large copies land in pinned host memory from torch's caching
+    host allocator (fast DMA, no per-call page pinning after the first use); the array keeps the
+    pinned block alive and returns it to the cache when it is garbage collected."""
+    t = torch()
+    tensor = tensor.detach()
+    if tensor.is_cuda and tensor.numel() * tensor.element_size() >= (1 << 20):
+        tensor = tensor.contiguous()
+        host = t.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
+        host.copy_(tensor, non_blocking=True)
+        t.cuda.current_stream(tensor.device).synchronize()
+        return host.numpy()
+    return tensor.cpu().numpy()
 
 
 def soa(**tensors):
