@@ -413,7 +413,7 @@ class BiasCorr(dv.LazyArrays):
         if self._replay_mode():
             t = self._orbit_on_device()
             pm = t["primary_mass"]
-            rv = dv.empty((nstars, max_ep, ns), "float64", dev)
+            rv = dv.zeros((nstars, max_ep, ns), "float64", dev)
             drv = dv.empty((nstars, ns), "float64", dev)
             with dv.DeviceGuard(dev):
                 _abi.check(_abi.lib().rvmc_biascorr_replay_f64(
@@ -461,7 +461,7 @@ class BiasCorr(dv.LazyArrays):
         else:
             if "rv_host" not in c:
                 nstars, ns = self.number_of_stars, int(self.number_of_samples)
-                rvd = dv.empty((nstars, c["max_ep"], ns), "float32", self._device)
+                rvd = dv.zeros((nstars, c["max_ep"], ns), "float32", self._device)
                 self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], 20, 4, None, None, rvd,
                                    None, None)
                 c["rv_host"] = dv.to_host(rvd).astype(np.float64)

@@ -327,7 +327,7 @@ __global__ void kepler_epochs_f64_kernel(int n_epochs, int64_t n_samples, const 
         const int64_t i = t % n_samples;
         double resid;
         E_out[t] = kepler_f64(mean_anomaly_epoch_f64(td[t], period[i], quirk), ecc[i], resid);
-        bad += (fabs(resid) > 1e-9) ? 1u : 0u;
+        bad += (fabs(resid) <= 1e-9) ? 0u : 1u;      // NaN counts as a failure
     }
     if (nonconverged && bad) atomicAdd(nonconverged, bad);
 }

@@ -223,7 +223,13 @@ struct OrbitF64 {
 };
 
 RVMC_HD double powerlaw_f64(const PowerLaw<double>& pl, double u) {
+    // np.random.uniform(low, high) is low + (high-low)*u with separate roundings: no FMA
+    // contraction here, so the materialised arrays equal NumPy's bit for bit for exponents 1 and 2
+#if defined(__CUDA_ARCH__)
+    const double p = __dadd_rn(pl.a, __dmul_rn(pl.b, u));
+#else
     const double p = pl.a + pl.b * u;
+#endif
     // exponents 1 and 2 (kappa = 0, pi = e_power = -0.5: the Sana et al. defaults) need no pow()
     const double y = (pl.kind == POW_ONE) ? p : (pl.kind == POW_TWO) ? p * p : pow(p, pl.inv);
     return y * pl.minv;

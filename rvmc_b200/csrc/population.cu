@@ -44,7 +44,7 @@ __global__ void sample_orbits_kernel(PopF64 P, uint64_t seed, uint64_t first_ite
         if (out.eccentric_anomaly) {
             double resid;
             out.eccentric_anomaly[i] = kepler_f64(RVMC_TWO_PI * o.time / o.period, o.eccentricity, resid);
-            bad += (fabs(resid) > 1e-9) ? 1u : 0u;
+            bad += (fabs(resid) <= 1e-9) ? 0u : 1u;      // NaN counts as a failure
         }
     }
     if (nonconverged && bad) atomicAdd(nonconverged, bad);
@@ -79,7 +79,7 @@ __global__ void kepler_f64_kernel(int64_t n, const double* __restrict__ time, co
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double resid;
         E_out[i] = kepler_f64(RVMC_TWO_PI * time[i] / period[i], ecc[i], resid);
-        bad += (fabs(resid) > 1e-9) ? 1u : 0u;   // also true for NaN inputs
+        bad += (fabs(resid) <= 1e-9) ? 0u : 1u;      // NaN counts as a failure
     }
     if (nonconverged && bad) atomicAdd(nonconverged, bad);
 }

@@ -422,10 +422,10 @@ static int make_fused_point(const rvmc_pop_params& p, uint64_t seed, FusedPoint*
     RVMC_REQUIRE(p.fbin >= 0.0 && p.fbin <= 1.0, "fbin must be in [0,1] (got %g)", p.fbin);
     RVMC_REQUIRE(p.kepler_iters >= 1 && p.kepler_iters <= 8, "kepler_iters must be in [1,8] (got %d)",
                  p.kepler_iters);
-    RVMC_REQUIRE(p.min_period > 1.0 && p.max_period > p.min_period,
-                 "need 1 d < min_period < max_period (the law is in log10 P, RVMC.py:134)");
-    RVMC_REQUIRE(p.min_mass > 0 && p.max_mass > p.min_mass && p.min_q > 0 && p.max_q > p.min_q,
-                 "need 0 < min < max for the mass and mass-ratio ranges");
+    RVMC_REQUIRE(p.min_period > 1.0 && p.max_period >= p.min_period,
+                 "need 1 d < min_period <= max_period (the law is in log10 P, RVMC.py:134)");
+    RVMC_REQUIRE(p.min_mass > 0 && p.max_mass >= p.min_mass && p.min_q > 0 && p.max_q >= p.min_q,
+                 "need 0 < min <= max for the mass and mass-ratio ranges");
     out->seed_lo = (uint32_t)seed;
     out->seed_hi = (uint32_t)(seed >> 32);
     out->coin_thresh = (uint32_t)llrint(p.fbin * 16777216.0);

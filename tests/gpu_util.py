@@ -22,8 +22,18 @@ def stream():
     return dv.stream_ptr(dev())
 
 
+_KEEP = []
+
+
 def up(a, dtype):
-    return dv.to_device(np.asarray(a), dtype, dev())
+    """Upload and KEEP ALIVE until the end of the test: `dv.ptr(up(x))` inline would otherwise
+    free the tensor before the (asynchronous) kernel reads it."""
+    t = dv.to_device(np.asarray(a), dtype, dev())
+    _KEEP.append(t)
+    if len(_KEEP) > 256:
+        dv.torch().cuda.synchronize()
+        del _KEEP[:128]
+    return t
 
 
 def empty(shape, dtype):
