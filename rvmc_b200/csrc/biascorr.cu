@@ -28,8 +28,10 @@ namespace rvmc {
 struct BcArgs {
     PopF32 P32;
     PopF64 P64;
-    uint64_t seed, noise_seed;
+    PhiloxKey key, noise_key;     // expanded on the host: round keys are constant-bank operands
+    uint64_t seed;                // (kept for the fp64 mass draw)
     int32_t nstars, max_epochs;
+    int32_t star0;                // first star of this launch (gridDim.y is limited to 65535)
     const int32_t* n_epochs;      // [nstars]
     const double* t_obs;          // [nstars][max_epochs]  s
     const float* rv_err;          // [nstars][max_epochs]  km/s, or nullptr
@@ -41,7 +43,6 @@ struct BcArgs {
     float delta_rv_min, n_sigma;
     uint64_t first_sample;
     int64_t n_samples, sample_stride;
-    int64_t blocks_per_star;
     float* delta_rv;              // [nstars][sample_stride]
     uint8_t* detected;            // [nstars][sample_stride]
     float* rv_out;                // [nstars][max_epochs][sample_stride]
@@ -67,8 +68,8 @@ __device__ __forceinline__ double bc_mass_f64(const PopF64& P, int mode, const d
 }
 
 // Noise normals of epochs 4g..4g+3 of one binary.
-__device__ __forceinline__ void bc_noise4_f32(uint64_t seed, uint64_t item, uint32_t stream, int g, float z[4]) {
-    const u32x4 w = philox_block(seed, item, stream, (uint32_t)g);
+__device__ __forceinline__ void bc_noise4_f32(const PhiloxKey& K, uint64_t item, uint32_t stream, int g, float z[4]) {
+    const u32x4 w = philox_block(K, item, stream, (uint32_t)g);
     box_muller_f32(w.x, w.y, z[0], z[1]);
     box_muller_f32(w.z, w.w, z[2], z[3]);
 }
@@ -78,7 +79,11 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
     box_muller_f64(w.z, w.w, z[2], z[3]);
 }
 
-template <int NE>
+// NE    : compile-time bound on the epochs per star (<= 16: epoch loop fully unrolled, RVs in registers)
+// ITERS : Halley steps after the starter as a compile-time constant (0 = run-time a.kepler_iters)
+// LEAN  : the headline configuration -- measurement errors given, per-epoch RVs not written --
+//         with those two run-time switches resolved at compile time
+template <int NE, int ITERS, bool LEAN>
 __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     __shared__ double A_s[NE];            // 2 pi t_obs (quirk) or t_obs (physical)
     __shared__ float err_s[NE];
@@ -86,10 +91,11 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     __shared__ int uniform_s;
     __shared__ unsigned int c_det, c_guard, c_bad;
 
-    const int star = (int)(blockIdx.x / a.blocks_per_star);
-    const int64_t i = (int64_t)(blockIdx.x - (int64_t)star * a.blocks_per_star) * BC_THREADS + threadIdx.x;
+    const int star = a.star0 + (int)blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * BC_THREADS + threadIdx.x;
     const int ne = a.n_epochs[star];
-    const bool noisy = a.rv_err != nullptr;
+    const bool noisy = LEAN ? true : (a.rv_err != nullptr);
+    float* const rv_out = LEAN ? nullptr : a.rv_out;
 
     if (threadIdx.x < ne) {
         const double t = a.t_obs[(size_t)star * a.max_epochs + threadIdx.x];
@@ -122,8 +128,8 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     if (valid) {
         const uint64_t sample = a.first_sample + (uint64_t)i;
         const uint64_t item = bc_item(star, sample);
-        const u32x4 wa = philox_block(a.seed, item, RVMC_STREAM_ORBIT_A, 0);
-        const u32x4 wb = philox_block(a.seed, item, RVMC_STREAM_ORBIT_B, 0);
+        const u32x4 wa = philox_block(a.key, item, RVMC_STREAM_ORBIT_A, 0);
+        const u32x4 wb = philox_block(a.key, item, RVMC_STREAM_ORBIT_B, 0);
 
         // ---- per-binary quantities --------------------------------------------------------------
         OrbitF32 o;
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
         float vmax = -INFINITY, vmin = INFINITY;
         float z[4];
         auto epoch = [&](int k) {
-            if (noisy && (k & 3) == 0) bc_noise4_f32(a.noise_seed, item, RVMC_STREAM_EPOCH, k >> 2, z);
+            if (noisy && (k & 3) == 0) bc_noise4_f32(a.noise_key, item, RVMC_STREAM_EPOCH, k >> 2, z);
             float M;
             double M64;
             bool neg = false;
@@ -184,8 +190,8 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
                 M = (float)M64;
             }
             int g, b;
-            const float shape = kepler_shape_f32(M, M64, neg, o.e, rome2, sw, cw, a.kepler_iters,
-                                                 a.P32.guard_amp, g, b);
+            const float shape = kepler_shape_f32<ITERS>(M, M64, neg, o.e, rome2, sw, cw, a.kepler_iters,
+                                                        a.P32.guard_amp, g, b);
             my_guard += g;
             my_bad += b;
             float rv = K * shape;
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
             rvs[k] = rv;
             vmax = fmaxf(vmax, rv);
             vmin = fminf(vmin, rv);
-            if (a.rv_out) a.rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
+            if (rv_out) rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
         };
         if constexpr (NE <= 16) {
             // fully unrolled: rvs[] and z[] live in registers
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     if (my_bad) atomicAdd(&c_bad, my_bad);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int64_t first = (int64_t)(blockIdx.x - (int64_t)star * a.blocks_per_star) * BC_THREADS;
+        const int64_t first = (int64_t)blockIdx.x * BC_THREADS;
         const int64_t nvalid = min((int64_t)BC_THREADS, a.n_samples - first);
         if (a.counters) {
             atomicAdd(a.counters + 0, (unsigned long long)(nvalid * ne));
@@ -244,6 +250,31 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
             if (c_bad) atomicAdd(a.counters + 3, (unsigned long long)c_bad);
         }
         if (a.det_per_star && c_det) atomicAdd(a.det_per_star + star, c_det);
+    }
+}
+
+template <int NE, int ITERS, bool LEAN>
+static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
+    // gridDim.y carries the star (<= 65535 per launch)
+    for (int s0 = 0; s0 < a.nstars; s0 += 65535) {
+        a.star0 = s0;
+        const int ny = a.nstars - s0 < 65535 ? a.nstars - s0 : 65535;
+        biascorr_fused_kernel<NE, ITERS, LEAN><<<dim3((unsigned int)blocks_per_star, (unsigned int)ny), BC_THREADS, 0,
+                                                stream>>>(a);
+        RVMC_LAUNCH_CHECK();
+    }
+    return RVMC_OK;
+}
+
+template <int NE>
+static int bc_dispatch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
+    const bool lean = a.rv_err != nullptr && a.rv_out == nullptr;
+    if constexpr (NE <= 8) {
+        if (a.kepler_iters == 1)
+            return lean ? bc_launch<NE, 1, true>(a, blocks_per_star, stream) : bc_launch<NE, 1, false>(a, blocks_per_star, stream);
+        return lean ? bc_launch<NE, 0, true>(a, blocks_per_star, stream) : bc_launch<NE, 0, false>(a, blocks_per_star, stream);
+    } else {
+        return bc_launch<NE, 0, false>(a, blocks_per_star, stream);
     }
 }
 
@@ -440,9 +471,11 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
     if (nstars == 0 || n_samples == 0) return RVMC_OK;
     RVMC_REQUIRE(t_obs != nullptr, "t_obs is required");
     a.seed = seed;
-    a.noise_seed = noise_seed;
+    a.key = philox_key(seed);
+    a.noise_key = philox_key(noise_seed);
     a.nstars = nstars;
     a.max_epochs = max_epochs;
+    a.star0 = 0;
     a.n_epochs = n_epochs;
     a.t_obs = t_obs;
     a.rv_err = rv_err;
@@ -456,26 +489,21 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
     a.first_sample = first_sample;
     a.n_samples = n_samples;
     a.sample_stride = sample_stride;
-    a.blocks_per_star = (n_samples + BC_THREADS - 1) / BC_THREADS;
     a.delta_rv = delta_rv;
     a.detected = detected;
     a.rv_out = rv_out;
     a.counters = (unsigned long long*)counters;
     a.det_per_star = det_per_star;
-    const int64_t blocks = a.blocks_per_star * nstars;
-    if (blocks > 0x7fffffffLL) {
-        set_error("too many blocks in one launch (%lld); shard the samples", (long long)blocks);
+    const int64_t blocks_per_star = (n_samples + BC_THREADS - 1) / BC_THREADS;
+    if (blocks_per_star > 0x7fffffffLL) {
+        set_error("too many samples in one launch (%lld); shard them", (long long)n_samples);
         return RVMC_ERR_UNSUPPORTED;
     }
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (max_epochs <= 8)
-        biascorr_fused_kernel<8><<<(unsigned int)blocks, BC_THREADS, 0, stream>>>(a);
-    else if (max_epochs <= 16)
-        biascorr_fused_kernel<16><<<(unsigned int)blocks, BC_THREADS, 0, stream>>>(a);
-    else      // 17..64 epochs: same code with run-time loops (rvs[] in local memory)
-        biascorr_fused_kernel<64><<<(unsigned int)blocks, BC_THREADS, 0, stream>>>(a);
-    RVMC_LAUNCH_CHECK();
-    return RVMC_OK;
+    if (max_epochs <= 6) return bc_dispatch<6>(a, blocks_per_star, stream);
+    if (max_epochs <= 8) return bc_dispatch<8>(a, blocks_per_star, stream);
+    if (max_epochs <= 16) return bc_dispatch<16>(a, blocks_per_star, stream);
+    return bc_dispatch<64>(a, blocks_per_star, stream);      // 17..64 epochs: run-time loops, RVs in local memory
 }
 
 int rvmc_biascorr_sample(const rvmc_pop_params* p, uint64_t seed, int nstars, int mass_mode, const double* masses,

@@ -4,18 +4,22 @@
 // findBestDistributions.py:29-30 and the weighted formula of RVMC.py:262-268.
 //
 // A tile holds `nr` realizations of S stars, row-major.  Each realization is reduced by an
-// aligned sub-warp group of G lanes (G = largest power of two <= min(S, 32)) with xor-shuffles,
-// in two passes (mean, then squared deviations): the values already sit in shared memory, so the
-// second pass costs one more LDS per star and avoids the cancellation of a one-pass formula.
-// The summation order is fixed => results are bit-reproducible across launches and GPUs.
+// aligned group of G lanes, G a power of two chosen so that the tile keeps every thread of the
+// block busy: G = 1 (one thread sums its whole row, no shuffles) for the small clusters that
+// dominate the workloads (S <= 16), up to a full warp for S >= ~170.  One pass: the sums of
+// d = v - pivot and d^2 are accumulated with the row's first star as pivot, which keeps the
+// fp32 cancellation in  var = (sum d^2 - (sum d)^2 / S) / (S - ddof)  harmless (the pivot is a
+// sample of the distribution, so |mean - pivot| ~ sigma).  The summation order is fixed =>
+// results are bit-reproducible across launches and GPUs.
 #pragma once
 #include <stdint.h>
 
 namespace rvmc {
 
-inline int reduce_group_size(int S) {
+// threads: block size; R: realizations per tile.  Smallest power of two G with R*G >= threads.
+inline int reduce_group_size(int S, int R, int threads) {
     int g = 1;
-    while (g * 2 <= S && g * 2 <= 32) g *= 2;
+    while (g < 32 && (int64_t)R * g < threads && g * 2 <= S) g *= 2;
     return g;
 }
 
@@ -39,29 +43,37 @@ __device__ __forceinline__ void reduce_tile_sigma(const T* v, int nr, int S, int
         const int r = it * ng + gi;
         const bool valid = r < nr;
         const T* row = v + (size_t)(valid ? r : 0) * S;
-        T acc = 0;
-        if (wts) {
-            for (int j = gl; j < S; j += G) acc += wts[j] * row[j];
-        } else {
-            for (int j = gl; j < S; j += G) acc += row[j];
-        }
-        acc = group_sum(acc, G);
-        const T mean = wts ? acc / wsum : acc / (T)S;
-        T acc2 = 0;
+        const T pivot = row[0];
+        T s1 = 0, s2 = 0;
         if (wts) {
             for (int j = gl; j < S; j += G) {
-                const T d = row[j] - mean;
-                acc2 += wts[j] * d * d;
+                const T d = row[j] - pivot;
+                const T wd = wts[j] * d;
+                s1 += wd;
+                s2 = fma(wd, d, s2);
             }
         } else {
             for (int j = gl; j < S; j += G) {
-                const T d = row[j] - mean;
-                acc2 += d * d;
+                const T d = row[j] - pivot;
+                s1 += d;
+                s2 = fma(d, d, s2);
             }
         }
-        acc2 = group_sum(acc2, G);
+        if (G > 1) {
+            s1 = group_sum(s1, G);
+            s2 = group_sum(s2, G);
+        }
         if (valid && gl == 0) {
-            const T var = wts ? acc2 / wsum : acc2 / (T)(S - ddof);   // S == ddof -> 0/0 = NaN like NumPy
+            T var;
+            if (wts) {
+                // sum w (v - mu)^2 / sum w  with  mu = pivot + s1 / wsum            (RVMC.py:263-268)
+                const T m = s1 / wsum;
+                var = s2 / wsum - m * m;
+            } else {
+                // S == ddof -> 0/0 = NaN like NumPy
+                var = (s2 - s1 * s1 / (T)S) / (T)(S - ddof);
+            }
+            var = var < (T)0 ? (T)0 : var;       // rounding can leave -0.0...: keep sqrt real (NaN stays NaN)
             out[r] = (OutT)sqrt(var);
         }
     }

@@ -104,7 +104,9 @@ RVMC_HD float semi_amplitude_f32(const PopF32& P, const OrbitF32& o) {
 // Markley (1995) cubic starter (|error| < 5e-4 rad for every e < 1) followed by `iters` Halley
 // steps; the iteration count is a launch-uniform constant, so a warp never diverges here.
 // Returns E and its sin/cos (angle-addition update of the last evaluated pair).
-RVMC_HD float kepler_f32(float M, float e, int iters, float& sE, float& cE, float& resid) {
+template <int ITERS = 0>
+RVMC_HD float kepler_f32(float M, float e, int iters_rt, float& sE, float& cE, float& resid) {
+    const int iters = ITERS > 0 ? ITERS : iters_rt;      // ITERS > 0: fully unrolled, no loop overhead
     const float pi = 3.14159265358979f;
     const float ome = 1.0f - e;
     const float alpha = fmaf(5.026548245743669f * (pi - M), fast_rcp(1.0f + e), 29.608813203268074f) *
@@ -122,7 +124,7 @@ RVMC_HD float kepler_f32(float M, float e, int iters, float& sE, float& cE, floa
     E = (M == 0.0f) ? 0.0f : E;                                   // 0/0 guard at the exact origin
     float s, c, f = 0.0f;
     sincos_rad(E, s, c);
-#pragma unroll 1
+#pragma unroll(ITERS > 0 ? ITERS : 1)
     for (int it = 0; it < iters; ++it) {
         f = fmaf(-e, s, E) - M;
         const float fp = fmaf(-e, c, 1.0f);
@@ -172,10 +174,11 @@ RVMC_HD float rv_shape_f32(float e, float rome2, float sE, float cE, float sw, f
 // the amplification of an error in M into the true anomaly, sqrt(1-e^2)/(1-e cos E)^2, exceeds
 // guard_amp: only for e > ~0.9, i.e. never with the reference's hard-coded bounds (RVMC.py:158).
 // `guard` / `bad` report the guard path and a residual above 1e-5 (SciPy's RuntimeWarning).
+template <int ITERS = 0>
 RVMC_HD float kepler_shape_f32(float M, double M64, bool neg, float e, float rome2, float sw, float cw,
                                int iters, float guard_amp, int& guard, int& bad) {
     float sE, cE, resid;
-    const float E = kepler_f32(M, e, iters, sE, cE, resid);
+    const float E = kepler_f32<ITERS>(M, e, iters, sE, cE, resid);
     const float dd = fmaf(-e, cE, 1.0f);
     if (dd * dd * guard_amp < rome2) {
         double E64 = (double)E, s64, c64;
@@ -196,6 +199,7 @@ RVMC_HD float kepler_shape_f32(float M, double M64, bool neg, float e, float rom
 
 // Full single-epoch orbital RV of one sampled orbit [km/s]; the sign of the phase folds M into
 // [0, pi].
+template <int ITERS = 0>
 RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float* K_out, int& guard,
                            int& bad) {
     const float K = semi_amplitude_f32(P, o);
@@ -203,7 +207,7 @@ RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float*
     float sw, cw;
     sincos_turn(o.wturn, sw, cw);
     const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
-    const float shape = kepler_shape_f32(6.283185307179586f * aphase, RVMC_TWO_PI * (double)aphase,
+    const float shape = kepler_shape_f32<ITERS>(6.283185307179586f * aphase, RVMC_TWO_PI * (double)aphase,
                                          o.phase < 0.0f, o.e, rome2, sw, cw, iters, P.guard_amp, guard, bad);
     if (K_out) *K_out = K;
     return K * shape;

@@ -48,6 +48,47 @@ RVMC_HD u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {
     return c;
 }
 
+// Expanded key schedule: the ten round keys of a seed.  Kernels take it as a launch parameter so
+// that every round key is a constant-bank operand of the LOP3 that consumes it, instead of two
+// integer adds per round per thread.
+struct PhiloxKey {
+    uint32_t k0[10], k1[10];
+};
+
+RVMC_HD PhiloxKey philox_key(uint64_t seed) {
+    PhiloxKey K;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k0[r] = a;
+        K.k1[r] = b;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    return K;
+}
+
+RVMC_HD u32x4 philox_block(const PhiloxKey& K, uint64_t item, uint32_t stream, uint32_t sub) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    u32x4 c;
+    c.x = (uint32_t)item;
+    c.y = (uint32_t)(item >> 32);
+    c.z = stream;
+    c.w = sub;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c.x, hi0, lo0);
+        mulhilo32(M1, c.z, hi1, lo1);
+        u32x4 n;
+        n.x = hi1 ^ c.y ^ K.k0[r];
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ K.k1[r];
+        n.w = lo0;
+        c = n;
+    }
+    return c;
+}
+
 // One block for (item, stream, sub) under a 64-bit seed.
 RVMC_HD u32x4 philox_block(uint64_t seed, uint64_t item, uint32_t stream, uint32_t sub) {
     u32x4 c;

@@ -404,7 +404,7 @@ int rvmc_sigma1d_pool(uint64_t seed, uint32_t call_id, const double* pool, int64
     const int S = sample_size;
     const int T = 2048;                                  // star slots per tile (16 KB of fp64)
     const int R = S >= T ? 1 : T / S;
-    const int G = reduce_group_size(S);
+    const int G = reduce_group_size(S, R, 256);
     const size_t smem = ((size_t)R * S + 2 * (size_t)S) * sizeof(double);
     if (smem > 48 * 1024)
         RVMC_CUDA(cudaFuncSetAttribute(sigma1d_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -36,6 +36,7 @@ struct FusedPoint {
 
 struct FusedArgs {
     FusedPoint single;         // the population when points == nullptr (single-population launch)
+    PhiloxKey key;             // its expanded key schedule (constant-bank operands of the Philox rounds)
     const FusedPoint* points;  // device, one per grid point, or nullptr
     const float* meas_err;     // device [S]
     float* sigma_out;          // [n_points][sigma_stride]
@@ -56,7 +57,12 @@ __device__ __forceinline__ float slot_scale(float sigma_dyn, float err) {
     return sqrtf(fmaf(sigma_dyn, sigma_dyn, err * err));
 }
 
-__global__ void __launch_bounds__(256) sigma1d_fused_kernel(FusedArgs a) {
+// SINGLE: one population for the whole launch, read straight from the kernel parameters (constant
+//         bank: no staging, no registers spent on it, pre-expanded Philox keys); otherwise one
+//         descriptor per grid point, staged in shared memory.
+// ITERS : Halley steps as a compile-time constant (0 = run-time kepler_iters).
+template <bool SINGLE, int ITERS>
+__global__ void __launch_bounds__(256, 3) sigma1d_fused_kernel(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S;
     const int T = a.R * S;
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(256) sigma1d_fused_kernel(FusedArgs a) {
     float* scale = v + T;                                        // [S]
     float* wts = scale + S;                                      // [S]
     uint16_t* queue = reinterpret_cast<uint16_t*>(wts + S);      // [T]
-    __shared__ FusedPoint pt;
+    __shared__ FusedPoint pt_s;
     __shared__ int qn;
     __shared__ float wsum_s;
     __shared__ unsigned int cnt_guard, cnt_bad;
@@ -76,13 +82,12 @@ __global__ void __launch_bounds__(256) sigma1d_fused_kernel(FusedArgs a) {
     const int nslots = nr * S;
 
     // stage the point descriptor and the per-star tables
-    if (a.points) {
+    if (!SINGLE) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.points + point);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&pt);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&pt_s);
         for (int i = threadIdx.x; i < (int)(sizeof(FusedPoint) / 4); i += blockDim.x) dst[i] = src[i];
-    } else if (threadIdx.x == 0) {
-        pt = a.single;
     }
+    const FusedPoint& pt = SINGLE ? a.single : pt_s;
     if (threadIdx.x == 0) {
         qn = 0;
         cnt_guard = 0;
@@ -102,6 +107,9 @@ __global__ void __launch_bounds__(256) sigma1d_fused_kernel(FusedArgs a) {
     }
 
     const uint64_t seed = seed_of(pt);
+    auto draw = [&](uint64_t item, uint32_t stream) {
+        return SINGLE ? philox_block(a.key, item, stream, 0) : philox_block(seed, item, stream, 0);
+    };
     const uint64_t slot0 = (a.first_real + (uint64_t)r0) * (uint64_t)S;
     const uint64_t p_begin = slot0 >> 1;
     const int npairs = (int)(((slot0 + nslots + 1) >> 1) - p_begin);
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(256) sigma1d_fused_kernel(FusedArgs a) {
         int l0 = 0, l1 = 0;
         if (pi < npairs) {
             const uint64_t pair = p_begin + pi;
-            const u32x4 w = philox_block(seed, pair, RVMC_STREAM_SLOT, 0);
+            const u32x4 w = draw(pair, RVMC_STREAM_SLOT);
             float z0, z1;
             box_muller_f32(w.z, w.w, z0, z1);
             const int64_t la = (int64_t)(2 * pair - slot0);
@@ -152,11 +160,11 @@ __global__ void __launch_bounds__(256) sigma1d_fused_kernel(FusedArgs a) {
     for (int k = threadIdx.x; k < nq; k += blockDim.x) {
         const int l = queue[k];
         const uint64_t slot = slot0 + (uint64_t)l;
-        const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, 0);
-        const u32x4 wb = philox_block(seed, slot, RVMC_STREAM_ORBIT_B, 0);
+        const u32x4 wa = draw(slot, RVMC_STREAM_ORBIT_A);
+        const u32x4 wb = draw(slot, RVMC_STREAM_ORBIT_B);
         const OrbitF32 o = sample_orbit_f32(pt.pop, wa, wb);
         int g, b;
-        const float rv = orbit_rv_f32(pt.pop, o, pt.kepler_iters, nullptr, g, b);
+        const float rv = orbit_rv_f32<ITERS>(pt.pop, o, pt.kepler_iters, nullptr, g, b);
         v[l] += rv;
         my_guard += g;
         my_bad += b;
@@ -422,10 +430,11 @@ static int make_fused_point(const rvmc_pop_params& p, uint64_t seed, FusedPoint*
     RVMC_REQUIRE(p.fbin >= 0.0 && p.fbin <= 1.0, "fbin must be in [0,1] (got %g)", p.fbin);
     RVMC_REQUIRE(p.kepler_iters >= 1 && p.kepler_iters <= 8, "kepler_iters must be in [1,8] (got %d)",
                  p.kepler_iters);
-    RVMC_REQUIRE(p.min_period > 1.0 && p.max_period >= p.min_period,
-                 "need 1 d < min_period <= max_period (the law is in log10 P, RVMC.py:134)");
-    RVMC_REQUIRE(p.min_mass > 0 && p.max_mass >= p.min_mass && p.min_q > 0 && p.max_q >= p.min_q,
-                 "need 0 < min <= max for the mass and mass-ratio ranges");
+    // the power law is in log10(P/day) (RVMC.py:134): periods <= 1 d give log10 <= 0 and NaNs in the
+    // reference.  min > max is not an error there (the law simply runs backwards).
+    RVMC_REQUIRE(p.min_period > 1.0 && p.max_period > 1.0, "min_period and max_period must be > 1 day (RVMC.py:134)");
+    RVMC_REQUIRE(p.min_mass > 0 && p.max_mass > 0 && p.min_q > 0 && p.max_q > 0,
+                 "mass and mass-ratio bounds must be > 0");
     out->seed_lo = (uint32_t)seed;
     out->seed_hi = (uint32_t)(seed >> 32);
     out->coin_thresh = (uint32_t)llrint(p.fbin * 16777216.0);
@@ -449,7 +458,7 @@ static int fused_tile_shape(int S, TileShape* ts) {
     }
     const int T = 4096;
     ts->R = S >= T ? 1 : T / S;
-    ts->G = reduce_group_size(S);
+    ts->G = reduce_group_size(S, ts->R, 256);
     const size_t slots = (size_t)ts->R * S;
     ts->smem = slots * sizeof(float) + 2 * (size_t)S * sizeof(float) + slots * sizeof(uint16_t) + 16;
     return RVMC_OK;
@@ -457,15 +466,15 @@ static int fused_tile_shape(int S, TileShape* ts) {
 
 static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, int64_t n_points, const float* meas_err, int S, int weighted,
                         int ddof, uint64_t first_real, int64_t n_real, float* sigma_out, int64_t sigma_stride,
-                        uint64_t* counters, cudaStream_t stream) {
+                        uint64_t* counters, bool iters1, cudaStream_t stream) {
     TileShape ts;
     int rc = fused_tile_shape(S, &ts);
     if (rc) return rc;
-    if (ts.smem > 48 * 1024)
-        RVMC_CUDA(cudaFuncSetAttribute(sigma1d_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)ts.smem));
     FusedArgs a;
-    if (single) a.single = *single;
+    if (single) {
+        a.single = *single;
+        a.key = philox_key(((uint64_t)single->seed_hi << 32) | single->seed_lo);
+    }
     a.points = d_points;
     a.meas_err = meas_err;
     a.sigma_out = sigma_out;
@@ -485,9 +494,17 @@ static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, in
         return RVMC_ERR_UNSUPPORTED;
     }
     a.tiles_per_point = (int32_t)tiles_per_point;
-    sigma1d_fused_kernel<<<(unsigned int)total, 256, ts.smem, stream>>>(a);
-    RVMC_LAUNCH_CHECK();
-    return RVMC_OK;
+    // kepler_iters is launch-uniform for a single population; a grid takes the run-time count unless
+    // the caller guarantees 1 everywhere (iters1)
+    auto go = [&](auto kernel) -> int {
+        if (ts.smem > 48 * 1024)
+            RVMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem));
+        kernel<<<(unsigned int)total, 256, ts.smem, stream>>>(a);
+        RVMC_LAUNCH_CHECK();
+        return RVMC_OK;
+    };
+    if (single) return single->kepler_iters == 1 ? go(sigma1d_fused_kernel<true, 1>) : go(sigma1d_fused_kernel<true, 0>);
+    return iters1 ? go(sigma1d_fused_kernel<false, 1>) : go(sigma1d_fused_kernel<false, 0>);
 }
 
 }  // namespace rvmc
@@ -517,7 +534,7 @@ int rvmc_sigma1d_fused(const rvmc_pop_params* p, uint64_t seed, const float* mea
     for (int64_t done = 0; done < n_real; done += max_real) {
         const int64_t chunk = (n_real - done < max_real) ? n_real - done : max_real;
         rc = launch_fused(&fp, nullptr, 1, meas_err, sample_size, weighted, ddof, first_real + done, chunk,
-                          sigma_out + done, 0, counters, stream);
+                          sigma_out + done, 0, counters, false, stream);
         if (rc) return rc;
     }
     return RVMC_OK;
@@ -566,9 +583,11 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     cudaStream_t stream = (cudaStream_t)cuda_stream;
 
     std::vector<FusedPoint> host(n_points);
+    bool iters1 = true;
     for (int64_t i = 0; i < n_points; ++i) {
         rc = make_fused_point(points[i].pop, points[i].seed, &host[i]);
         if (rc) return rc;
+        iters1 = iters1 && host[i].kepler_iters == 1;
     }
     // stream-ordered scratch for the descriptors: no library-global state, so concurrent calls on
     // different streams do not interact
@@ -591,7 +610,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         const int64_t np = (n_points - p0 < batch) ? n_points - p0 : batch;
         float* sig = sigma_out ? sigma_out + (size_t)p0 * n_real : scratch;
         rc = launch_fused(nullptr, d_points + p0, np, meas_err, sample_size, weighted, ddof, 0, n_real, sig, n_real,
-                          counters, stream);
+                          counters, iters1, stream);
         if (rc) break;
         StatsArgs sa;
         sa.sigma = sig;
