@@ -559,8 +559,10 @@ int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const float* meas_
 }
 
 int rvmc_grid_scratch_slots(int device) {
+    // one launch pair (fused kernel + statistics kernel) per batch of this many points: four
+    // statistics blocks per SM keep every SM busy for two waves (148 SMs x 2 resident blocks)
     (void)device;
-    return 128;
+    return 592;
 }
 
 int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* meas_err, int sample_size,

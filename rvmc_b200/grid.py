@@ -32,6 +32,42 @@ STATS_DTYPE = np.dtype([("mode", "f8"), ("mean", "f8"), ("median", "f8"), ("p05"
                         ("n_nonconverged", "u4"), ("n_hist_bins", "u4"), ("reserved", "u4")])
 assert STATS_DTYPE.itemsize == C.sizeof(_abi.PointStats) == 80
 
+# rvmc_grid_point as a NumPy record, so that 10^4-10^5 grid points are built by broadcasting instead
+# of one ctypes object per point
+POINT_DTYPE = np.dtype([(n, "f8") for n, t in _abi.PopParams._fields_ if t is C.c_double] +
+                       [("kepler_iters", "i4"), ("reserved", "i4"), ("seed", "u8")])
+assert POINT_DTYPE.itemsize == C.sizeof(_abi.GridPoint)
+POP_FIELDS = tuple(n for n, t in _abi.PopParams._fields_ if t is C.c_double)
+
+
+def points_array(n, **columns):
+    """Record array of n grid points filled with the reference defaults (RVMC.py:28-43), then the
+    given columns (scalars or length-n arrays of any rvmc_pop_params field, or `seed`)."""
+    d = _abi.PopParams.defaults()
+    a = np.empty(int(n), dtype=POINT_DTYPE)
+    for f in POP_FIELDS:
+        a[f] = getattr(d, f)
+    a["kepler_iters"], a["reserved"], a["seed"] = d.kepler_iters, 0, 0
+    for k, v in columns.items():
+        if k not in POINT_DTYPE.names:
+            raise TypeError("unknown population parameter %r" % k)
+        a[k] = v
+    return a
+
+
+def _as_points(pops, seeds):
+    if isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE:
+        a = pops.copy()
+        if seeds is not None:
+            a["seed"] = np.asarray(seeds, dtype=np.uint64)
+        return a
+    a = np.empty(len(pops), dtype=POINT_DTYPE)
+    raw = a.view(np.uint8).reshape(len(pops), POINT_DTYPE.itemsize)
+    for i, p in enumerate(pops):
+        raw[i, :C.sizeof(_abi.PopParams)] = np.frombuffer(bytes(p), dtype=np.uint8)
+    a["seed"] = np.asarray(seeds, dtype=np.uint64)
+    return a
+
 
 # ---------------------------------------------------------------------------------------------
 # sharding + gathering (host logic; exercised on CPU with gloo in tests/test_distributed_cpu.py)
@@ -85,7 +121,13 @@ def point_seeds(seed, n_points, common_random_numbers=False):
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     if common_random_numbers:
         return [seed] * n_points
-    return [dv.splitmix64((seed + 0x632BE59BD9B4E019 * (i + 1)) & 0xFFFFFFFFFFFFFFFF) for i in range(n_points)]
+    with np.errstate(over="ignore"):
+        x = np.uint64(seed) + np.uint64(0x632BE59BD9B4E019) * np.arange(1, n_points + 1, dtype=np.uint64)
+        x = x + np.uint64(0x9E3779B97F4A7C15)                       # splitmix64, vectorised (wraps mod 2^64)
+        z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return [int(v) for v in z]
 
 
 def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**5, bin=0.5, ddof=0,
@@ -98,25 +140,24 @@ def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**
     (uint32 [n_points, hist_bins] or None, same remark), 'counters' (binary RVs, guard,
     non-converged of THIS rank), 'local' (indices this rank computed)."""
     n_points = len(pops)
-    if len(seeds) != n_points:
+    if seeds is not None and len(seeds) != n_points:
         raise ValueError("need one seed per grid point")
     err = np.ascontiguousarray(measured_errors, dtype=np.float32)
     if err.ndim != 1 or err.size != int(sample_size):
         raise ValueError("measured_errors must have sample_size = %d entries (got shape %s)"
                          % (int(sample_size), err.shape))
-    for p in pops:
-        if -1.0 in (p.mass_power, p.period_pi, p.mass_ratio_kappa, p.e_power):
+    all_pts = _as_points(pops, seeds)
+    for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
+        if np.any(all_pts[f] == -1.0):
             raise ZeroDivisionError("float division by zero")          # RVMC.py:112
     rank, world = dist_info(group) if distributed else (0, 1)
     local = shard_indices(n_points, rank, world)
     dev = dv.resolve_device(device)
     t = dv.torch()
     ns = int(number_of_samples)
-    pts = (_abi.GridPoint * max(len(local), 1))()
-    for k, i in enumerate(local):
-        pts[k].pop = pops[i]
-        pts[k].seed = seeds[i]
     nl = len(local)
+    pts_np = np.ascontiguousarray(all_pts[local]) if nl else np.zeros(1, dtype=POINT_DTYPE)
+    pts = pts_np.ctypes.data_as(C.POINTER(_abi.GridPoint))
     stats_d = dv.zeros((max(nl, 1) * STATS_DTYPE.itemsize,), "uint8", dev)
     errd = dv.to_device(err, "float32", dev)
     counters = dv.zeros((4,), "int64", dev)
@@ -391,9 +432,9 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
     shape = tuple(len(v) for v in vals)
     mesh = np.meshgrid(*vals, indexing="ij")
     flat = [m.ravel() for m in mesh]
-    base = dict(base or {})
-    pops = [_abi.PopParams.defaults(**dict(base, **{k: float(f[i]) for k, f in zip(names, flat)}))
-            for i in range(int(np.prod(shape)))]
+    cols = dict(base or {})
+    cols.update({k: f for k, f in zip(names, flat)})
+    pops = points_array(int(np.prod(shape)), **cols)
     res = run_points(pops, point_seeds(seed, len(pops), common_random_numbers), _errs(measured_errors, sample_size),
                      sample_size, number_of_samples, bin=bin, ddof=ddof, device=device, group=group)
     out = dict(axes=dict(zip(names, vals)), shape=shape, stats=res["stats"].reshape(shape), counters=res["counters"],
