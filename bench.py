@@ -218,7 +218,7 @@ def run_gpu_arm(args):
     cnt = dv.zeros((4,), "int64", dev)
 
     def step():
-        _abi.check(lib.rvmc_biascorr_fused(C.byref(p), seed, noise_seed, nstars, 6, dv.ptr(d_nep), dv.ptr(d_tobs),
+        _abi.check(lib.rvmc_biascorr_fused(C.byref(p), seed, noise_seed, 0, nstars, 6, dv.ptr(d_nep), dv.ptr(d_tobs),
                                            dv.ptr(d_err), 0, None, None, 1, 20.0, 4.0, first_sample, ns, ns,
                                            dv.ptr(drv), dv.ptr(det), None, dv.ptr(cnt), None, st))
 
@@ -348,7 +348,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--stars", type=int, default=100)

@@ -201,7 +201,10 @@ RVMC_API int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const flo
 /* ---- K5 fused: multi-epoch Delta-RV + significance (BiasCorr, RVMC_bias_corr.py:406-476) ----
  * Binary (star, sample), samples [first_sample, first_sample+n_samples) of every star; `seed`
  * keys the orbit draws (the same numbers rvmc_biascorr_sample materialises), `noise_seed` the
- * measurement errors (a fresh one per calculate_radial_velocities() call).  t_obs: device float64[nstars*max_epochs] (row i holds n_epochs[i] valid entries, s);
+ * measurement errors (a fresh one per calculate_radial_velocities() call).  `first_star` is the
+ * global index of the first star of this call: every array below is indexed from it (star
+ * s of the call is global star first_star + s), so stars can be sharded over calls, streams or
+ * GPUs without changing any value.  t_obs: device float64[nstars*max_epochs] (row i holds n_epochs[i] valid entries, s);
  * rv_err: device float32[nstars*max_epochs] per-epoch errors in km/s or NULL (no noise, no
  * detection); mass_mode 0 = IMF (RVMC_bias_corr.py:205-207), 1 = N(masses, mass_errors) (:183),
  * 2 = masses at face value (:190); masses/mass_errors: device float64[nstars], kg.
@@ -210,7 +213,8 @@ RVMC_API int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const flo
  * uint8[nstars*n_samples] (:451-476), rv_out float32[nstars*max_epochs*n_samples] (the noisy
  * radial_velocities, :419-421), counters uint64[4] = {binary-epoch RVs, detected, guard,
  * non-converged} (accumulated), det_per_star uint32[nstars] (accumulated). */
-RVMC_API int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int nstars, int max_epochs,
+RVMC_API int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int first_star,
+                        int nstars, int max_epochs,
                         const int32_t* n_epochs, const double* t_obs, const float* rv_err,
                         int mass_mode, const double* masses, const double* mass_errors,
                         int quirk_phase, float delta_rv_min, float n_sigma,

@@ -93,7 +93,7 @@ SIGNATURES = {
     "rvmc_sigma1d_pool": (_I, [_U64, _U32, _VP, _I64, _VP, _I, _I, _I, _U64, _I64, _VP, _VP]),
     "rvmc_sigma1d_fused": (_I, [C.POINTER(PopParams), _U64, _VP, _I, _I, _I, _U64, _I64, _VP, _VP, _VP]),
     "rvmc_fused_trace": (_I, [C.POINTER(PopParams), _U64, _VP, _I, _U64, _I64, TraceSoA, _VP]),
-    "rvmc_biascorr_fused": (_I, [C.POINTER(PopParams), _U64, _U64, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _I, _F,
+    "rvmc_biascorr_fused": (_I, [C.POINTER(PopParams), _U64, _U64, _I, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _I, _F,
                                  _F, _U64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rvmc_biascorr_sample": (_I, [C.POINTER(PopParams), _U64, _I, _I, _VP, _VP, _U64, _I64, _U32, OrbitSoA, _VP]),
     "rvmc_kepler_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _I, _VP, _VP, _VP]),

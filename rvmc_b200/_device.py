@@ -81,6 +81,29 @@ def to_host(tensor):
     return tensor.cpu().numpy()
 
 
+_copy_streams = {}
+
+
+def to_host_overlapped(tensor, chunks):
+    """Rows of a [nstars, ...] device tensor -> one pinned NumPy array, copied chunk by chunk on a
+    side stream as soon as the kernel that produced each chunk has finished.  `chunks` is a list of
+    (row0, row1, event) with `event` recorded after that chunk's kernel: the D2H transfer of chunk
+    k overlaps the compute of chunks k+1.. (the copy engine and the SMs work concurrently)."""
+    t = torch()
+    dev = tensor.device
+    key = (dev.type, dev.index)
+    if key not in _copy_streams:
+        _copy_streams[key] = t.cuda.Stream(device=dev)
+    cs = _copy_streams[key]
+    host = t.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
+    with t.cuda.stream(cs):
+        for r0, r1, ev in chunks:
+            cs.wait_event(ev)
+            host[r0:r1].copy_(tensor[r0:r1], non_blocking=True)
+    cs.synchronize()
+    return host.numpy()
+
+
 def soa(**tensors):
     """rvmc_orbit_soa from keyword tensors (missing = NULL)."""
     s = _abi.OrbitSoA()

@@ -137,7 +137,7 @@ class BiasCorr(dv.LazyArrays):
         self._rv_user = None                          # user-assigned radial_velocities
         self.fbin = fbin
         self.delta_rv_single = None
-        self._set_device("delta_rv", dv.zeros((nstars, ns), "float32", self._device))     # :251
+        # delta_rv = np.zeros(shape) at :251 -- materialised only if it is read before the first RV pass
 
     # ---- plumbing -------------------------------------------------------------------------------
     def _next_seed(self):
@@ -160,6 +160,9 @@ class BiasCorr(dv.LazyArrays):
                 return d[name]
             elif name == "radial_velocities":
                 return self._radial_velocities_list()
+            elif name == "delta_rv" and not self._has(name):
+                self._set_device("delta_rv", dv.zeros((self.number_of_stars, int(self.number_of_samples)), "float32",
+                                                      self._device))
         return dv.LazyArrays.__getattr__(self, name)
 
     def __setattr__(self, name, value):
@@ -430,24 +433,39 @@ class BiasCorr(dv.LazyArrays):
         det = dv.empty((nstars, ns), "uint8", dev) if d_err is not None else None
         counters = dv.zeros((4,), "int64", dev)
         per_star = dv.zeros((max(nstars, 1),), "int32", dev)
-        self._launch_fused(nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, None, counters, per_star)
+        # large problems go out as a few launches over star ranges: the copy of one range's results
+        # to the host (get_detected_binaries) then overlaps the compute of the next ranges
+        n_chunks = min(nstars, 8) if nstars * ns >= 4_000_000 else 1
+        bounds = np.linspace(0, nstars, max(n_chunks, 1) + 1).astype(int)
+        chunks = []
+        t = dv.torch()
+        for s0, s1 in zip(bounds[:-1], bounds[1:]):
+            if s1 > s0:
+                self._launch_fused(nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, None, counters,
+                                   per_star, stars=(int(s0), int(s1)))
+                ev = t.cuda.Event()
+                ev.record(t.cuda.current_stream(dev))
+                chunks.append((int(s0), int(s1), ev))
         self._rv_cache = dict(mode="fused", nep=nep, max_ep=max_ep, d_nep=d_nep, d_tobs=d_tobs, d_err=d_err,
-                              det={(float(delta_RV), float(n_sigma_RV)): det} if det is not None else {},
+                              det={(float(delta_RV), float(n_sigma_RV)): (det, chunks)} if det is not None else {},
                               counters=counters, per_star=per_star)
         self._set_device("delta_rv", drv)
 
     def _launch_fused(self, nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
-                      per_star, first_sample=0, n_samples=None):
+                      per_star, stars=None):
         dev = self._device
-        nstars = self.number_of_stars
-        ns = int(self.number_of_samples) if n_samples is None else int(n_samples)
+        ns = int(self.number_of_samples)
+        s0, s1 = (0, self.number_of_stars) if stars is None else stars
         m, me = self._mass_tables()
+
+        def rows(x):
+            return None if x is None else x[s0:s1]
         with dv.DeviceGuard(dev):
             _abi.check(_abi.lib().rvmc_biascorr_fused(
-                C.byref(self._pop()), self._seed0, self._rv_seed, nstars, max_ep, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err),
-                self._mass_mode, dv.ptr(m), dv.ptr(me), 0 if self.physical_phase else 1, float(delta_RV),
-                float(n_sigma_RV), int(first_sample), ns, ns, dv.ptr(drv), dv.ptr(det), dv.ptr(rv_out),
-                dv.ptr(counters), dv.ptr(per_star), dv.stream_ptr(dev)))
+                C.byref(self._pop()), self._seed0, self._rv_seed, s0, s1 - s0, max_ep, dv.ptr(rows(d_nep)),
+                dv.ptr(rows(d_tobs)), dv.ptr(rows(d_err)), self._mass_mode, dv.ptr(rows(m)), dv.ptr(rows(me)),
+                0 if self.physical_phase else 1, float(delta_RV), float(n_sigma_RV), 0, ns, ns, dv.ptr(rows(drv)),
+                dv.ptr(rows(det)), dv.ptr(rows(rv_out)), dv.ptr(counters), dv.ptr(rows(per_star)), dv.stream_ptr(dev)))
 
     def _radial_velocities_list(self):
         """`radial_velocities`: list of (n_epochs_i, n_samples) arrays (RVMC_bias_corr.py:250,419-421)."""
@@ -528,8 +546,11 @@ class BiasCorr(dv.LazyArrays):
             det = dv.empty((nstars, ns), "uint8", dev)
             self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], delta_RV, n_sigma_RV, None,
                                det, None, None, None)
-            c["det"][key] = det
-        return dv.to_host(c["det"][key]).view(np.bool_)
+            c["det"][key] = (det, None)
+        det, chunks = c["det"][key]
+        if chunks and len(chunks) > 1:
+            return dv.to_host_overlapped(det, chunks).view(np.bool_)
+        return dv.to_host(det).view(np.bool_)
 
     def detection_counts(self):
         """Additive helper: per-star detected counts and the global counters of the last fused pass

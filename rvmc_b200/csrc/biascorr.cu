@@ -32,6 +32,7 @@ struct BcArgs {
     uint64_t seed;                // (kept for the fp64 mass draw)
     int32_t nstars, max_epochs;
     int32_t star0;                // first star of this launch (gridDim.y is limited to 65535)
+    int32_t first_star;           // global index of local star 0 (RNG counter only)
     const int32_t* n_epochs;      // [nstars]
     const double* t_obs;          // [nstars][max_epochs]  s
     const float* rv_err;          // [nstars][max_epochs]  km/s, or nullptr
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     bool det = false;
     if (valid) {
         const uint64_t sample = a.first_sample + (uint64_t)i;
-        const uint64_t item = bc_item(star, sample);
+        const uint64_t item = bc_item(a.first_star + star, sample);
         const u32x4 wa = philox_block(a.key, item, RVMC_STREAM_ORBIT_A, 0);
         const u32x4 wb = philox_block(a.key, item, RVMC_STREAM_ORBIT_B, 0);
 
@@ -441,7 +442,8 @@ static int bc_check_common(const rvmc_pop_params* p, int nstars, int max_epochs,
 
 extern "C" {
 
-int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int nstars, int max_epochs,
+int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int first_star, int nstars,
+                        int max_epochs,
                         const int32_t* n_epochs, const double* t_obs, const float* rv_err, int mass_mode,
                         const double* masses, const double* mass_errors, int quirk_phase, float delta_rv_min,
                         float n_sigma, uint64_t first_sample, int64_t n_samples, int64_t sample_stride,
@@ -451,6 +453,7 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
     int rc = bc_check_common(p, nstars, max_epochs, n_epochs);
     if (rc) return rc;
     RVMC_REQUIRE(n_samples >= 0, "number_of_samples must be >= 0");
+    RVMC_REQUIRE(first_star >= 0 && (int64_t)first_star + nstars <= (1 << 24), "star index must stay below 2^24");
     RVMC_REQUIRE(sample_stride >= n_samples, "sample_stride must be >= n_samples");
     RVMC_REQUIRE(mass_mode >= 0 && mass_mode <= 2, "mass_mode must be 0, 1 or 2");
     RVMC_REQUIRE(mass_mode == 0 || masses != nullptr, "masses are required for mass_mode %d", mass_mode);
@@ -476,6 +479,7 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
     a.nstars = nstars;
     a.max_epochs = max_epochs;
     a.star0 = 0;
+    a.first_star = first_star;
     a.n_epochs = n_epochs;
     a.t_obs = t_obs;
     a.rv_err = rv_err;

@@ -74,7 +74,7 @@ def _fused(p, seed, noise_seed, t_obs, rv_errors, ns, first=0, mass_mode=0, mass
     per = g.zeros((nstars,), "int32")
     m = None if masses is None else g.up(masses, "float64")
     me = None if mass_errors is None else g.up(mass_errors, "float64")
-    g.ok(g.lib().rvmc_biascorr_fused(C.byref(p), seed, noise_seed, nstars, max_ep, dv.ptr(d_nep), dv.ptr(d_tobs),
+    g.ok(g.lib().rvmc_biascorr_fused(C.byref(p), seed, noise_seed, 0, nstars, max_ep, dv.ptr(d_nep), dv.ptr(d_tobs),
                                      dv.ptr(d_err), mass_mode, dv.ptr(m), dv.ptr(me), quirk, dRV, nsig, first, ns, ns,
                                      dv.ptr(drv), dv.ptr(det), dv.ptr(rv), dv.ptr(cnt), dv.ptr(per), g.stream()))
     return dict(drv=g.host(drv), det=g.host(det).astype(bool), rv=None if rv is None else g.host(rv), cnt=g.host(cnt),
@@ -238,11 +238,11 @@ def test_biascorr_errors():
     nep, max_ep, d_nep, d_tobs, d_err = _tables([DAYS6], [2.0])
     L = g.lib()
     drv = g.empty((1, 8), "float32")
-    rc = L.rvmc_biascorr_fused(C.byref(p), 1, 1, 1, 70, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0, None, None, 1,
+    rc = L.rvmc_biascorr_fused(C.byref(p), 1, 1, 0, 1, 70, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0, None, None, 1,
                                20.0, 4.0, 0, 8, 8, dv.ptr(drv), None, None, None, None, g.stream())
     assert rc == _abi.RVMC_ERR_UNSUPPORTED
-    rc = L.rvmc_biascorr_fused(C.byref(p), 1, 1, 1, 6, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 1, None, None, 1,
+    rc = L.rvmc_biascorr_fused(C.byref(p), 1, 1, 0, 1, 6, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 1, None, None, 1,
                                20.0, 4.0, 0, 8, 8, dv.ptr(drv), None, None, None, None, g.stream())
     assert rc == _abi.RVMC_ERR_INVALID and b"masses" in L.rvmc_last_error()
-    g.ok(L.rvmc_biascorr_fused(C.byref(p), 1, 1, 1, 6, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0, None, None, 1,
+    g.ok(L.rvmc_biascorr_fused(C.byref(p), 1, 1, 0, 1, 6, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0, None, None, 1,
                                20.0, 4.0, 0, 0, 0, None, None, None, None, None, g.stream()))

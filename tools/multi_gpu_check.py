@@ -62,7 +62,7 @@ def main():
     def run(first, n):
         drv = dv.empty((nstars, n), "float32", dev)
         det = dv.empty((nstars, n), "uint8", dev)
-        _abi.check(lib.rvmc_biascorr_fused(C.byref(p), 5, 6, nstars, 6, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0,
+        _abi.check(lib.rvmc_biascorr_fused(C.byref(p), 5, 6, 0, nstars, 6, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0,
                                            None, None, 1, 20.0, 4.0, first, n, n, dv.ptr(drv), dv.ptr(det), None, None,
                                            None, dv.stream_ptr(dev)))
         return drv, det

@@ -31,7 +31,7 @@ if what in ("biascorr", "all"):
     det = dv.empty((nstars, ns), "uint8", dev)
     cnt = dv.zeros((4,), "int64", dev)
     for _ in range(4):
-        _abi.check(lib.rvmc_biascorr_fused(C.byref(p), 1, 2, nstars, 6, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0,
+        _abi.check(lib.rvmc_biascorr_fused(C.byref(p), 1, 2, 0, nstars, 6, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0,
                                            None, None, 1, 20.0, 4.0, 0, ns, ns, dv.ptr(drv), dv.ptr(det), None,
                                            dv.ptr(cnt), None, st))
     torch.cuda.synchronize()
