@@ -62,7 +62,7 @@ __device__ __forceinline__ float slot_scale(float sigma_dyn, float err) {
 //         descriptor per grid point, staged in shared memory.
 // ITERS : Halley steps as a compile-time constant (0 = run-time kepler_iters).
 template <bool SINGLE, int ITERS>
-__global__ void __launch_bounds__(256, 3) sigma1d_fused_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(256, 4) sigma1d_fused_kernel(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S;
     const int T = a.R * S;
@@ -307,32 +307,50 @@ __global__ void __launch_bounds__(STATS_THREADS) point_stats_kernel(StatsArgs a)
         const int ng = n_groups;
         const bool do_mode = (pass == 1) && nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX;
         const double last_edge = (double)nb_mode * a.bin;
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const float x = sig[i];
+        const float inv_bin = (float)(1.0 / a.bin);
+        // pass 0 run-length cache: nearly every element shares its top byte, so a thread flushes a
+        // counter to the shared histogram only when the byte changes
+        unsigned int run_digit = 0xffffffffu, run_count = 0;
+        auto visit = [&](float x) {
             const unsigned int bits = __float_as_uint(x);
             const unsigned int digit = (bits >> shift) & 255u;
-            const unsigned int high = (pass == 0) ? 0u : (bits >> (shift + 8));
             if (pass == 0) {
                 sum += (double)x;
                 mx = max(mx, bits);
-                // nearly every element shares its top byte: aggregate equal digits inside the warp
-                const unsigned int peers = __match_any_sync(__activemask(), digit);
-                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[0][digit], __popc(peers));
+                if (digit != run_digit) {
+                    if (run_count) atomicAdd(&hist[0][run_digit], run_count);
+                    run_digit = digit;
+                    run_count = 0;
+                }
+                ++run_count;
             } else {
+                const unsigned int high = bits >> (shift + 8);
                 for (int g = 0; g < ng; ++g)
                     if (high == group_prefix[g]) atomicAdd(&hist[g][digit], 1u);
             }
             if (do_mode) {
                 // edges are k*bin (np.arange(0, max+bin, bin)); bin k = [k*bin, (k+1)*bin), the last
-                // bin is closed on the right (np.histogram)
+                // bin is closed on the right (np.histogram).  fp32 guess, exact fp64 correction.
                 const double xd = (double)x;
-                int k = (int)floor(xd / a.bin);
+                int k = (int)(x * inv_bin);
                 if ((double)k * a.bin > xd) --k;
                 else if ((double)(k + 1) * a.bin <= xd) ++k;
                 if (k >= nb_mode && xd <= last_edge) k = nb_mode - 1;
                 if (k >= 0 && k < nb_mode) atomicAdd(&mode_hist[k], 1u);
             }
+        };
+        // four independent loads in flight per thread
+        int64_t i = threadIdx.x;
+        for (; i + 3 * (int64_t)blockDim.x < n; i += 4 * (int64_t)blockDim.x) {
+            const float x0 = __ldg(sig + i), x1 = __ldg(sig + i + blockDim.x), x2 = __ldg(sig + i + 2 * blockDim.x),
+                        x3 = __ldg(sig + i + 3 * blockDim.x);
+            visit(x0);
+            visit(x1);
+            visit(x2);
+            visit(x3);
         }
+        for (; i < n; i += blockDim.x) visit(__ldg(sig + i));
+        if (pass == 0 && run_count) atomicAdd(&hist[0][run_digit], run_count);
         if (pass == 0) {
             atomicMax(&max_bits, mx);
             sum = block_sum_f64(sum, red);       // contains the barriers
@@ -605,14 +623,31 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     const FusedPoint* d_points = (const FusedPoint*)ws;
 
     const int64_t tiles_per_point = (n_real + ts.R - 1) / ts.R;
-    int64_t batch = rvmc_grid_scratch_slots(0);
+    int64_t batch = rvmc_grid_scratch_slots(0) / 2;               // the scratch is used as two halves
     if (sigma_out) batch = 0x7fff0000LL / tiles_per_point;       // no scratch limit: as many as one launch takes
     if (batch < 1) batch = 1;
-    for (int64_t p0 = 0; p0 < n_points; p0 += batch) {
+    // The statistics kernel of batch b runs on a side stream while the fused kernel of batch b+1
+    // runs on the caller's stream (scratch halves alternate), so its latency-bound passes hide
+    // behind the compute-bound Monte Carlo.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
+    rc = cuda_status(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
+    for (int k = 0; k < 2 && !rc; ++k)
+        rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
+    int64_t nb = 0;
+    for (int64_t p0 = 0; p0 < n_points && !rc; p0 += batch, ++nb) {
         const int64_t np = (n_points - p0 < batch) ? n_points - p0 : batch;
-        float* sig = sigma_out ? sigma_out + (size_t)p0 * n_real : scratch;
+        const int half = (int)(nb & 1);
+        float* sig = sigma_out ? sigma_out + (size_t)p0 * n_real : scratch + (size_t)half * batch * n_real;
+        // this scratch half was last read by the statistics kernel of batch nb-2
+        if (!sigma_out && nb >= 2) rc = cuda_status(cudaStreamWaitEvent(stream, ev_stats[half], 0), "cudaStreamWaitEvent");
+        if (rc) break;
         rc = launch_fused(nullptr, d_points + p0, np, meas_err, sample_size, weighted, ddof, 0, n_real, sig, n_real,
                           counters, iters1, stream);
+        if (rc) break;
+        rc = cuda_status(cudaEventRecord(ev_fused, stream), "cudaEventRecord");
+        if (!rc) rc = cuda_status(cudaStreamWaitEvent(side, ev_fused, 0), "cudaStreamWaitEvent");
         if (rc) break;
         StatsArgs sa;
         sa.sigma = sig;
@@ -622,10 +657,20 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         sa.hist_bins = hist_bins;
         sa.stats_out = stats_out + p0;
         sa.hist_out = hist_out ? hist_out + (size_t)p0 * hist_bins : nullptr;
-        point_stats_kernel<<<(unsigned int)np, STATS_THREADS, 0, stream>>>(sa);
+        point_stats_kernel<<<(unsigned int)np, STATS_THREADS, 0, side>>>(sa);
         rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
-        if (rc) break;
+        if (!rc) rc = cuda_status(cudaEventRecord(ev_stats[half], side), "cudaEventRecord");
     }
+    // the caller's stream continues only after every statistics kernel has finished
+    for (int k = 0; k < 2; ++k)
+        if (ev_stats[k] && nb > k) {
+            int rc2 = cuda_status(cudaStreamWaitEvent(stream, ev_stats[k], 0), "cudaStreamWaitEvent");
+            if (!rc) rc = rc2;
+        }
+    if (ev_fused) cudaEventDestroy(ev_fused);
+    for (int k = 0; k < 2; ++k)
+        if (ev_stats[k]) cudaEventDestroy(ev_stats[k]);
+    if (side) cudaStreamDestroy(side);       // deferred by the runtime until its work has drained
     cudaFreeAsync(ws, stream);
     return rc;
 }

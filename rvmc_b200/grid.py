@@ -483,3 +483,71 @@ def read_weighted_RVdisp_vs_age(path):
                              sig1D_err=float(parts[4])))
     assert header == ['name', 'age', 'age_err', 'sig1D', 'sig1D_err']
     return rows
+
+
+# ---------------------------------------------------------------------------------------------
+# P_min(age) relation (findBestDistributions.py:316-397) -- host post-processing of <= 10 points
+# ---------------------------------------------------------------------------------------------
+def quad_func(p, x):
+    """findBestDistributions.py:322-325 (despite its name: a * exp(-x / b) + c)."""
+    a, b, c = p
+    return a * np.exp(- x / b) + c
+
+
+def read_best_fit_table(path):
+    """One-row table written by find_best_Pmin / find_best_fbin -> dict name -> float."""
+    with open(path) as f:
+        names = f.readline().split()
+        vals = [float(v) for v in f.readline().split()]
+    return dict(zip(names, vals))
+
+
+def plot_Pmin_vs_age(fit=False, results_dir="results", age_table="data_RT20/weighted_RVdisp_vs_age.txt", plot=False):
+    """Joins the per-cluster best P_min files with the cluster ages (sigma rounded to 2 decimals,
+    findBestDistributions.py:350-359) and, with `fit=True`, fits P_min(t) = a exp(-t/b) + c by
+    orthogonal distance regression with a fixed to 1e5, 1e4 and 1e6 (:384-397).  Returns a dict with
+    the joined columns and the three (beta, sd_beta) pairs; `plot=True` draws the reference's figure."""
+    import glob
+    files = sorted(glob.glob(os.path.join(results_dir, 'Pmin_ObsSig_*_Nstars_*.dat')))
+    tabs = [read_best_fit_table(f) for f in files]
+    sig_file = np.array([float(os.path.basename(f).split('ObsSig_')[1].split('_Nstars')[0]) for f in files])
+    ages = read_weighted_RVdisp_vs_age(age_table)
+    cols = dict(name=[], age=[], age_err=[], sig1D=[], Pmin=[], Pmin016=[], Pmin084=[])
+    for i in range(len(files)):
+        for row in ages:
+            if round(sig_file[i], 2) == round(row["sig1D"], 2):
+                cols["name"].append(row["name"])
+                cols["age"].append(row["age"])
+                cols["age_err"].append(row["age_err"])
+                cols["sig1D"].append(row["sig1D"])
+                cols["Pmin"].append(tabs[i]["best_Pmin"])
+                cols["Pmin016"].append(tabs[i]["0.16perc_Pmin"])
+                cols["Pmin084"].append(tabs[i]["0.84perc_Pmin"])
+    out = {k: (np.array(v) if k != "name" else v) for k, v in cols.items()}
+    out["Pmin_errs"] = [out["Pmin"] - out["Pmin016"], out["Pmin084"] - out["Pmin"]]
+    if fit and len(out["age"]) >= 3:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from scipy import odr
+            sy = np.abs(out["Pmin_errs"][0] - out["Pmin_errs"][1])
+            sy = np.where(sy > 0, sy, np.min(sy[sy > 0]) if np.any(sy > 0) else 1.0)
+            data = odr.RealData(out["age"], out["Pmin"], sx=out["age_err"], sy=sy)
+            model = odr.Model(quad_func)
+            fits = {}
+            for a0 in (1e5, 1e4, 1e6):
+                res = odr.ODR(data, model, beta0=[a0, 0.2, 1.3], ifixb=[0, 1, 1]).run()
+                fits[a0] = dict(beta=res.beta, sd_beta=res.sd_beta)
+        out["fits"] = fits
+    if plot:
+        import matplotlib.pyplot as plt
+        fig = plt.figure(figsize=(4, 4))
+        plt.errorbar(out["age"], out["Pmin"], xerr=out["age_err"], yerr=out["Pmin_errs"], fmt='.', color='grey')
+        if "fits" in out:
+            x = np.linspace(0., 6, 1000)
+            plt.plot(x, quad_func(out["fits"][1e5]["beta"], x))
+        plt.yscale('log')
+        plt.xlabel('age (Myr)')
+        plt.ylabel(r'$\rm{P_{min}}$ (log days)')
+        out["figure"] = fig
+    return out

@@ -48,7 +48,15 @@ class RVMC(dv.LazyArrays):
     def __init__(self, number_of_stars=10**5, min_mass=6., max_mass=20., min_period=10.**0.15,
                  max_period=10.**3.5, period_pi=-0.5, mass_ratio_kappa=0, mass_power=-2.35, min_q=0.1,
                  max_q=1.0, e_power=-0.5, mass_dist=None, period_dist=None, sigma_dyn=2.0, fbin=0.7,
-                 seed=None, device=None):
+                 seed=None, device=None, **physics):
+        """`physics` (additive): the constants the reference hard-codes at RVMC.py:155-159
+        -- e_min, e_max_mid, e_max_long, p_circ_days, p_mid_days -- and the solver knobs
+        kepler_iters (Halley steps after the starter, default 1) and guard_amp."""
+        unknown = set(physics) - {"e_min", "e_max_mid", "e_max_long", "p_circ_days", "p_mid_days", "kepler_iters",
+                                  "guard_amp"}
+        if unknown:
+            raise TypeError("RVMC.__init__() got an unexpected keyword argument %r" % sorted(unknown)[0])
+        self._physics = dict(physics)
         # RVMC.py:64-77
         self.fbin = fbin
         self.min_mass = min_mass
@@ -116,6 +124,7 @@ class RVMC(dv.LazyArrays):
     def _pop(self, lenient=0, **overrides):
         """rvmc_pop_params from the CURRENT attribute values (the reference reads them at call time)."""
         kw = {k: float(getattr(self, a)) for k, a in _POP_FROM_ATTR.items()}
+        kw.update(self._physics)
         kw.update(overrides)
         if lenient & 1:           # mass_dist given: the IMF law is unused, keep it well-formed
             kw.update(min_mass=6.0, max_mass=20.0, mass_power=-2.35)

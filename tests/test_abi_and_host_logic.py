@@ -161,3 +161,23 @@ def test_data_rt20_readers(tmp_path):
         assert [r["Nstars"] for r in grid.read_Nstars_massRange(ref + "/Nstars_massRange.txt")] == \
             [8, 5, 14, 13, 9, 44, 16, 22, 332, 12]
         assert len(grid.read_weighted_RVdisp_vs_age(ref + "/weighted_RVdisp_vs_age.txt")) == 10
+
+
+def test_pmin_vs_age_join_and_fit(tmp_path):
+    """findBestDistributions.py:328-397: join on sigma rounded to 2 dp, ODR fit of a exp(-t/b) + c."""
+    age = tmp_path / "ages.txt"
+    rows = [("A", 1.0, 0.5, 10.123), ("B", 2.0, 0.5, 20.456), ("C", 3.0, 0.5, 30.789), ("D", 4.0, 0.6, 41.5),
+            ("E", 0.5, 0.2, 7.25)]
+    age.write_text("name ; age ; age_err ; sig1D ; sig1D_err\n" +
+                   "".join("%s ; %g ; %g ; %r ; 1.0\n" % r for r in rows) + "#F ; 9 ; 1 ; 99 ; 1\n")
+    for name, t, _, sig in rows:
+        pm = 1e5 * np.exp(-t / 0.4) + 2.0
+        grid._write_best(str(tmp_path / ("Pmin_ObsSig_%r_Nstars_12_Mass_6_20.dat" % sig)),
+                         ['best_Pmin', '0.05perc_Pmin', '0.16perc_Pmin', '0.84perc_Pmin', '0.95perc_Pmin'],
+                         [pm, pm * 0.5, pm * 0.8, pm * 1.3, pm * 2])
+    out = grid.plot_Pmin_vs_age(fit=True, results_dir=str(tmp_path), age_table=str(age))
+    assert sorted(out["name"]) == ["A", "B", "C", "D", "E"]
+    beta = out["fits"][1e5]["beta"]
+    assert beta[0] == 1e5 and abs(beta[1] - 0.4) < 1e-3 and abs(beta[2] - 2.0) < 1e-2
+    assert grid.quad_func([2.0, 1.0, 3.0], 0.0) == 5.0
+    assert grid.read_best_fit_table(str(tmp_path / "Pmin_ObsSig_10.123_Nstars_12_Mass_6_20.dat"))["best_Pmin"] > 0

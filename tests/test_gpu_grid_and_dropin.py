@@ -211,6 +211,20 @@ def test_rvmc_errors_and_custom_distributions():
     assert sps.kstest(cdf, "uniform").pvalue > 1e-3
 
 
+def test_rvmc_physics_knobs():
+    """the eccentricity regime constants (RVMC.py:155-159) as keyword arguments."""
+    c = RVMC(number_of_stars=50000, seed=3, e_max_mid=0.3, e_max_long=0.6, p_circ_days=10.0, p_mid_days=100.0)
+    P = c.period / 86400.0
+    e = c.eccentricity
+    assert np.all(e[P <= 10.0] == 0)
+    mid = (P > 10.0) & (P <= 100.0)
+    assert e[mid].max() <= 0.3 and e[mid].min() >= 1e-5 and e[P > 100.0].max() <= 0.6 and e[P > 100.0].max() > 0.5
+    s = c.subsample_fused(sample_size=12, number_of_samples=2000)
+    assert np.isfinite(s).all()
+    with pytest.raises(TypeError):
+        RVMC(number_of_stars=10, e_maximum=0.5)
+
+
 def test_biascorr_class_fused_and_replay_modes():
     t_obs = [DAYS6, DAYS6[:4], DAYS6]
     bc = BiasCorr(t_obs, number_of_samples=20000, rv_errors=[2.0, [1.0, 2.0, 1.5, 0.5], 3.0], seed=7)
