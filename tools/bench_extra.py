@@ -77,7 +77,7 @@ def main():
     fused_case("C1 S=100 1e4 realizations", P(), np.full(100, 1.2), 100, 10 ** 4)
     fused_case("C1 S=100 1e6 realizations", P(), np.full(100, 1.2), 100, 10 ** 6 // scale)
     # C5: grid points per second (sigma + on-device statistics), 1e5 realizations per point
-    npts = 1024 // scale
+    npts = 8192 // scale
     pi = np.linspace(-0.95, 0.5, 8)
     pops = [P(period_pi=float(pi[i % 8]), mass_ratio_kappa=-0.95 + 1.95 * ((i // 8) % 8) / 7.0,
               fbin=0.0625 + 0.9375 * ((i // 64) % 16) / 15.0) for i in range(npts)]
