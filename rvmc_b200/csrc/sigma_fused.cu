@@ -62,7 +62,7 @@ __device__ __forceinline__ float slot_scale(float sigma_dyn, float err) {
 //         descriptor per grid point, staged in shared memory.
 // ITERS : Halley steps as a compile-time constant (0 = run-time kepler_iters).
 template <bool SINGLE, int ITERS>
-__global__ void __launch_bounds__(256, 4) sigma1d_fused_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S;
     const int T = a.R * S;
