@@ -171,6 +171,36 @@ def golden_biascorr(ref_bc, name, seed, nsamples, mode):
     print(name, "draws:", len(rec.log), "detected frac:", detected.mean())
 
 
+def golden_distributions(ref_rvmc, ref_bc, name="reference_distributions"):
+    """Samples of the reference's OUTPUT DISTRIBUTIONS (its own RNG, nothing recorded) for the
+    two-sample KS legs of the parity protocol: sigma_1D of 12-star clusters bootstrapped from a
+    10^6-star pool (three binary fractions / period cut-offs), and Delta-RV + detection flags of the
+    6-epoch campaign.  float32 to keep the fixture small."""
+    out = {}
+    np.random.seed(20240607)
+    cases = [("fbin070_pmin14", dict(fbin=0.7, min_period=1.4, max_period=3500.)),
+             ("fbin028_pmin14", dict(fbin=0.28, min_period=1.4, max_period=3500.)),
+             ("fbin070_pmin30", dict(fbin=0.7, min_period=30.0, max_period=3500.))]
+    for tag, kw in cases:
+        c = ref_rvmc.RVMC(number_of_stars=10 ** 6, **kw)
+        c.calculate_binary_velocities()
+        out["sigma_" + tag] = np.asarray(c.subsample(sample_size=12, measured_errors=M17_ERRORS,
+                                                     number_of_samples=20000), dtype=np.float32)
+        out["sigma_w_" + tag] = np.asarray(c.subsample(sample_size=12, measured_errors=M17_ERRORS,
+                                                       number_of_samples=20000, weighted=True), dtype=np.float32)
+        out["rv_binary_" + tag] = np.asarray(c.rv_binary[:50000], dtype=np.float32)
+    days = np.array([0, 1, 7, 30, 180, 365.0]) * 86400
+    bc = ref_bc.BiasCorr([days, days], number_of_samples=20000, rv_errors=[2.0, [0.5, 3.0, 1.0, 2.0, 0.7, 1.5]])
+    bc.calculate_radial_velocities()
+    det = bc.get_detected_binaries(delta_RV=20, n_sigma_RV=4)
+    out["biascorr_delta_rv"] = np.asarray(bc.delta_rv, dtype=np.float32)
+    out["biascorr_detected_fraction"] = det.mean(axis=1)
+    out["biascorr_rv_errors_star1"] = np.array([0.5, 3.0, 1.0, 2.0, 0.7, 1.5])
+    out["m17_errors"] = M17_ERRORS
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: (float(np.median(v)) if v.ndim else float(v)) for k, v in out.items() if k.startswith(("sigma_f", "biascorr_det"))})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_rvmc, ref_bc = _import_reference()
@@ -185,6 +215,7 @@ def main():
                 n_real=64, sample_size=12)
     golden_biascorr(ref_bc, "biascorr_masses_ragged", seed=5, nsamples=192, mode="masses")
     golden_biascorr(ref_bc, "biascorr_imf_6epochs", seed=9, nsamples=256, mode="imf")
+    golden_distributions(ref_rvmc, ref_bc)
 
 
 if __name__ == "__main__":
