@@ -291,30 +291,41 @@ def run_gpu_arm(args):
                 ops, ms = C.c_double(), C.c_double()
                 _abi.check(lib.rvmc_pipe_peak(kind, 2000, C.byref(ops), C.byref(ms)))
                 pipes[name] = ops.value
-        roof = {"bound": "fp32", "achieved": rv_per_s_kernel * ALG_FP32_FLOP / 1e12, "unit": "TFLOP/s", "peak": None,
-                "frac": None, "traffic": args.traffic_bytes,
-                "kernel": "rvmc::biascorr_fused_kernel<6,1,true>", "launch_ms": launch_ms,
+        # Roofline of the dominant kernel.  The path has no dense contraction and writes < 1 B per unit,
+        # so neither the tensor cores nor HBM bound it: the SM instruction pipes do.
+        # achieved = ALGORITHMIC work per binary-epoch RV (100 FP32 flop + 17 SFU ops +
+        # 55 INT ops + 6 FP64 flop = 178 lane-instructions) x units/s of the CUDA-event timed launches;
+        # the binding ceiling is the issue rate (1 warp-instruction / clk / SM sub-partition), below the
+        # SFU (17 ops) and FP32 (100 flop) ceilings.  peak = SMs x 4 x 32 x SM clock sampled under load.
+        sms = C.c_int()
+        _abi.check(lib.rvmc_device_info(local, C.byref(sms), None, None, None))
+        clk_hz = 1e6 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+        alg_instr = ALG_FP32_FLOP + ALG_SFU_OPS + ALG_INT_OPS + ALG_FP64_FLOP
+        issue_peak = sms.value * 4 * 32 * clk_hz
+        roof = {"bound": "issue (instruction pipes; not hbm, not tensor)",
+                "achieved": rv_per_s_kernel * alg_instr / 1e12, "peak": issue_peak / 1e12,
+                "unit": "T lane-instr/s", "frac": rv_per_s_kernel * alg_instr / issue_peak,
+                "peak_source": "%d SMs x 4 schedulers x 32 lanes x %.0f MHz (NVML, sampled during the timed region)"
+                               % (sms.value, clk_hz / 1e6),
+                "traffic": args.traffic_bytes, "kernel": "rvmc::biascorr_fused_kernel<6,1,true>", "launch_ms": launch_ms,
                 "algorithmic_per_unit": {"fp32_flop": ALG_FP32_FLOP, "sfu_ops": ALG_SFU_OPS, "int_ops": ALG_INT_OPS,
-                                         "fp64_flop": ALG_FP64_FLOP, "hbm_bytes": ALG_HBM_BYTES},
-                "hbm": {"achieved_gbs": rv_per_s_kernel * ALG_HBM_BYTES / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
-                        "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback",
+                                         "fp64_flop": ALG_FP64_FLOP, "lane_instr": alg_instr, "hbm_bytes": ALG_HBM_BYTES},
+                "ncu": "profiles/r01_biascorr_fused_ncu.md: 80 % of issue slots busy, FMA 37 %, ALU 37 %, XU 41 %, "
+                       "FP64 9 %, tensor 0 %, DRAM 0.5 %",
+                "hbm": {"achieved": rv_per_s_kernel * ALG_HBM_BYTES / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "peak_source": "MEASURED_PEAKS.json" if peak_src == "measured" else "fallback 6650 GB/s",
                         "frac": rv_per_s_kernel * ALG_HBM_BYTES / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
         if pipes:
-            # Algorithmic work per unit x units/s against the pipe rates measured live on
-            # this device.  The larger fraction names the pipe that bounds the ALGORITHM; the committed
-            # ncu capture (profiles/) gives what the kernel actually issues (issue-slot utilisation).
-            fp32_peak = 2.0 * pipes["ffma"] / 1e12
-            fr = {"fp32": roof["achieved"] / fp32_peak,
-                  "sfu": rv_per_s_kernel * ALG_SFU_OPS / pipes["mufu"],
-                  "fp64": rv_per_s_kernel * ALG_FP64_FLOP / (2.0 * pipes["dfma"])}
-            roof.update({"peak": fp32_peak, "frac": fr["fp32"], "pipe_fracs": fr,
-                         "binding_pipe": max(fr, key=fr.get),
-                         "sfu": {"achieved": rv_per_s_kernel * ALG_SFU_OPS / 1e12, "peak": pipes["mufu"] / 1e12,
-                                 "unit": "T MUFU-op/s", "frac": fr["sfu"]},
-                         "peak_source": "measured live by rvmc_pipe_peak (FFMA / MUFU.EX2 / DFMA microbenchmarks on "
-                                        "this device at these clocks); MEASURED_PEAKS.json has no FP32/SFU figure",
-                         "pipe_peaks_lane_ops_per_s": pipes,
-                         "issue_slots_busy_ncu": "see profiles/ (ncu smsp__issue_active of the same kernel)"})
+            # the individual pipes, against rates measured live on this device by rvmc_pipe_peak
+            roof["fp32"] = {"achieved": rv_per_s_kernel * ALG_FP32_FLOP / 1e12, "peak": 2.0 * pipes["ffma"] / 1e12,
+                            "unit": "TFLOP/s", "frac": rv_per_s_kernel * ALG_FP32_FLOP / (2.0 * pipes["ffma"])}
+            roof["sfu"] = {"achieved": rv_per_s_kernel * ALG_SFU_OPS / 1e12, "peak": pipes["mufu"] / 1e12,
+                           "unit": "T MUFU-op/s", "frac": rv_per_s_kernel * ALG_SFU_OPS / pipes["mufu"]}
+            roof["fp64"] = {"achieved": rv_per_s_kernel * ALG_FP64_FLOP / 1e12, "peak": 2.0 * pipes["dfma"] / 1e12,
+                            "unit": "TFLOP/s", "frac": rv_per_s_kernel * ALG_FP64_FLOP / (2.0 * pipes["dfma"])}
+            roof["pipe_peaks_lane_ops_per_s"] = pipes
+            roof["pipe_peak_source"] = ("rvmc_pipe_peak microbenchmarks (FFMA, MUFU.EX2, IMAD.WIDE, DFMA, mixed issue) run "
+                                        "on this device in this process; MEASURED_PEAKS.json has no FP32/SFU figure")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 period/phase reduction)",

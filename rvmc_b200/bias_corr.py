@@ -151,7 +151,12 @@ class BiasCorr(dv.LazyArrays):
             if name in _ORBIT and name not in d["_host"] and name not in d["_dev"]:
                 self._materialize((name,))
             elif name in ("semi_major_axis", "max_orbital_velocity") and not self._has(name):
-                return None                                               # RVMC_bias_corr.py:246-247
+                if d.get("_rv_cache") is None:
+                    return None                                           # RVMC_bias_corr.py:246-247
+                # calculate_radial_velocities() leaves both behind in the reference (:412-413); the
+                # fused pass never needs them, so they are computed when first asked for
+                self.calculate_semi_major_axis()
+                self.calculate_max_orbital_velocity()
             elif name in ("min_mass", "max_mass") and d.get("_lazy_mass_range"):
                 pm = self._orbit_on_device(("primary_mass",))["primary_mass"]
                 object.__setattr__(self, "min_mass", float(pm.min().item()) / 2.e30)      # :186-187

@@ -194,6 +194,26 @@ def test_many_epochs_runtime_loop_variant():
     assert g.rel_err(clean["rv"][0, :40], want, K)[:, keep].max() < 1e-5
 
 
+def test_more_stars_than_one_grid_dimension():
+    """> 65535 stars are launched in several star ranges; first_star shards give identical values."""
+    p = _abi.PopParams.defaults()
+    nstars, ns = 70001, 3
+    t_obs = [DAYS6[:3]] * nstars
+    full = _fused(p, 8, 9, t_obs, 2.0, ns, want_rv=False)
+    assert np.isfinite(full["drv"]).all() and full["cnt"][0] == nstars * ns * 3
+    assert full["per"].sum() == full["det"].sum() == full["cnt"][1]
+    # the same stars in two calls with first_star offsets
+    nep, max_ep, d_nep, d_tobs, d_err = _tables(t_obs[:1000], 2.0)
+    parts = []
+    for s0, s1 in ((0, 400), (400, 1000)):
+        drv = g.empty((s1 - s0, ns), "float32")
+        g.ok(g.lib().rvmc_biascorr_fused(C.byref(p), 8, 9, s0, s1 - s0, max_ep, dv.ptr(d_nep[s0:s1]), dv.ptr(d_tobs[s0:s1]),
+                                         dv.ptr(d_err[s0:s1]), 0, None, None, 1, 20.0, 4.0, 0, ns, ns, dv.ptr(drv), None,
+                                         None, None, None, g.stream()))
+        parts.append(g.host(drv))
+    np.testing.assert_array_equal(np.concatenate(parts), full["drv"][:1000])
+
+
 def test_singles_delta_rv():
     nstars, n = 2, 40000
     errs = [np.array([1.0, 2.0, 0.5, 1.5, 1.0, 3.0]), np.array([2.0, 2.0, 2.0])]
