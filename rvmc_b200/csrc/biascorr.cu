@@ -84,7 +84,8 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
 // ITERS : Halley steps after the starter as a compile-time constant (0 = run-time a.kepler_iters)
 // LEAN  : the headline configuration -- measurement errors given, per-epoch RVs not written --
 //         with those two run-time switches resolved at compile time
-template <int NE, int ITERS, bool LEAN>
+// GUARD : keep the fp64 guard path (false when the host has proven it unreachable)
+template <int NE, int ITERS, bool LEAN, bool GUARD>
 __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     __shared__ double A_s[NE];            // 2 pi t_obs (quirk) or t_obs (physical)
     __shared__ float err_s[NE];
@@ -142,18 +143,19 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
             const double m = bc_mass_f64(a.P64, a.mass_mode, a.masses, a.mass_errors, star, a.seed, item, 0.0);
             o.log2m = fast_lg2((float)(m * (1.0 / RVMC_MSUN_KG)));     // m <= 0 -> NaN like the reference (Q12)
         }
-        // period in fp64: the phase needs ~1e-10 relative on P
+        // Period in fp64: the phase needs ~1e-10 relative on P (2 pi t / P reaches ~2e3 turns).  Only
+        // 1/P is ever needed: time = u P (RVMC_bias_corr.py:328), so t / P = t_obs / P + u, and the
+        // eccentricity regimes compare log10 P.
         const double xd = powerlaw_f64(a.P64.logp, u01_f64(wa.y));
-        const double P = RVMC_DAY_S * exp10(xd);
-        const double invP = 1.0 / P;
+        const double invP = exp10(-4.9365137424788932 - xd);            // 1 / (86400 * 10^x)  [1/s]
         o.x = (float)xd;
-        const double time = u01_f64(wa.z) * P;                          // RVMC_bias_corr.py:328
+        const double uphase = u01_f64(wa.z);
         o.q = powerlaw_f32(a.P32.q, u01_f32(wa.w));
         {
             const float ue = u01_f32(wb.x);
-            const bool is_long = P > a.P64.p_mid_s;                     // same compare as the fp64 arrays
+            const bool is_long = xd > a.P64.x_mid;
             const float e = powerlaw_f32(is_long ? a.P32.e_long : a.P32.e_mid, ue);
-            o.e = (P > a.P64.p_circ_s) ? e : 0.0f;
+            o.e = (xd > a.P64.x_circ) ? e : 0.0f;
         }
         o.cosi = u01_f32(wb.y);
         o.sini = fast_sqrt((1.0f - o.cosi) * (1.0f + o.cosi));
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
         float sw, cw;
         sincos_turn(o.wturn, sw, cw);
         const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
-        const double tw = a.quirk_phase ? RVMC_TWO_PI * time : time;
+        const double c0 = a.quirk_phase ? RVMC_TWO_PI * uphase : uphase;
 
         // ---- epochs -----------------------------------------------------------------------------
         float rvs[NE];
@@ -173,26 +175,21 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
             float M;
             double M64;
             bool neg = false;
-            const double arg = A_s[k] + tw;
+            // quirk (RVMC_bias_corr.py:357): ((2 pi t) mod P) / P == frac(2 pi t_obs / P + 2 pi u), in
+            // [0,1) and used as radians; physical: 2 pi frac(t_obs / P + u)
+            const double v = fma(A_s[k], invP, c0);
+            const double fr = v - floor(v);
             if (a.quirk_phase) {
-                // ((2 pi t) mod P) / P in [0,1), used as radians (RVMC_bias_corr.py:357)
-                const double kk = floor(arg * invP);
-                double m = fma(-kk, P, arg);
-                m = (m < 0.0) ? m + P : m;
-                m = (m >= P) ? m - P : m;
-                M64 = m * invP;
-                M = (float)M64;
+                M64 = fr;
             } else {
-                const double ph = arg * invP;
-                const double fr = ph - floor(ph);
                 const double fold = fr - rint(fr);                  // [-0.5, 0.5]
                 neg = fold < 0.0;
                 M64 = RVMC_TWO_PI * fabs(fold);
-                M = (float)M64;
             }
+            M = (float)M64;
             int g, b;
-            const float shape = kepler_shape_f32<ITERS>(M, M64, neg, o.e, rome2, sw, cw, a.kepler_iters,
-                                                        a.P32.guard_amp, g, b);
+            const float shape = kepler_shape_f32<ITERS, GUARD>(M, M64, neg, o.e, rome2, sw, cw, a.kepler_iters,
+                                                               a.P32.guard_amp, g, b);
             my_guard += g;
             my_bad += b;
             float rv = K * shape;
@@ -254,28 +251,34 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     }
 }
 
-template <int NE, int ITERS, bool LEAN>
+template <int NE, int ITERS, bool LEAN, bool GUARD>
 static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
     // gridDim.y carries the star (<= 65535 per launch)
     for (int s0 = 0; s0 < a.nstars; s0 += 65535) {
         a.star0 = s0;
         const int ny = a.nstars - s0 < 65535 ? a.nstars - s0 : 65535;
-        biascorr_fused_kernel<NE, ITERS, LEAN><<<dim3((unsigned int)blocks_per_star, (unsigned int)ny), BC_THREADS, 0,
-                                                stream>>>(a);
+        biascorr_fused_kernel<NE, ITERS, LEAN, GUARD>
+            <<<dim3((unsigned int)blocks_per_star, (unsigned int)ny), BC_THREADS, 0, stream>>>(a);
         RVMC_LAUNCH_CHECK();
     }
     return RVMC_OK;
 }
 
 template <int NE>
-static int bc_dispatch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
+static int bc_dispatch(BcArgs& a, bool guard, int64_t blocks_per_star, cudaStream_t stream) {
     const bool lean = a.rv_err != nullptr && a.rv_out == nullptr;
     if constexpr (NE <= 8) {
-        if (a.kepler_iters == 1)
-            return lean ? bc_launch<NE, 1, true>(a, blocks_per_star, stream) : bc_launch<NE, 1, false>(a, blocks_per_star, stream);
-        return lean ? bc_launch<NE, 0, true>(a, blocks_per_star, stream) : bc_launch<NE, 0, false>(a, blocks_per_star, stream);
+        if (a.kepler_iters == 1) {
+            if (!guard)
+                return lean ? bc_launch<NE, 1, true, false>(a, blocks_per_star, stream)
+                            : bc_launch<NE, 1, false, false>(a, blocks_per_star, stream);
+            return lean ? bc_launch<NE, 1, true, true>(a, blocks_per_star, stream)
+                        : bc_launch<NE, 1, false, true>(a, blocks_per_star, stream);
+        }
+        return lean ? bc_launch<NE, 0, true, true>(a, blocks_per_star, stream)
+                    : bc_launch<NE, 0, false, true>(a, blocks_per_star, stream);
     } else {
-        return bc_launch<NE, 0, false>(a, blocks_per_star, stream);
+        return bc_launch<NE, 0, false, true>(a, blocks_per_star, stream);
     }
 }
 
@@ -504,10 +507,11 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
         return RVMC_ERR_UNSUPPORTED;
     }
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (max_epochs <= 6) return bc_dispatch<6>(a, blocks_per_star, stream);
-    if (max_epochs <= 8) return bc_dispatch<8>(a, blocks_per_star, stream);
-    if (max_epochs <= 16) return bc_dispatch<16>(a, blocks_per_star, stream);
-    return bc_dispatch<64>(a, blocks_per_star, stream);      // 17..64 epochs: run-time loops, RVs in local memory
+    const bool guard = guard_reachable(*p);
+    if (max_epochs <= 6) return bc_dispatch<6>(a, guard, blocks_per_star, stream);
+    if (max_epochs <= 8) return bc_dispatch<8>(a, guard, blocks_per_star, stream);
+    if (max_epochs <= 16) return bc_dispatch<16>(a, guard, blocks_per_star, stream);
+    return bc_dispatch<64>(a, guard, blocks_per_star, stream);      // 17..64 epochs: run-time loops, RVs in local memory
 }
 
 int rvmc_biascorr_sample(const rvmc_pop_params* p, uint64_t seed, int nstars, int mass_mode, const double* masses,

@@ -174,13 +174,16 @@ RVMC_HD float rv_shape_f32(float e, float rome2, float sE, float cE, float sw, f
 // the amplification of an error in M into the true anomaly, sqrt(1-e^2)/(1-e cos E)^2, exceeds
 // guard_amp: only for e > ~0.9, i.e. never with the reference's hard-coded bounds (RVMC.py:158).
 // `guard` / `bad` report the guard path and a residual above 1e-5 (SciPy's RuntimeWarning).
-template <int ITERS = 0>
+// GUARD = false compiles the guard out: the host proves it unreachable when the largest
+// amplification the eccentricity bounds allow, sqrt(1-e^2)/(1-e)^2 at e_max, stays below guard_amp
+// (true for the reference's bounds: 43.6 at e = 0.9 against the default threshold 64).
+template <int ITERS = 0, bool GUARD = true>
 RVMC_HD float kepler_shape_f32(float M, double M64, bool neg, float e, float rome2, float sw, float cw,
                                int iters, float guard_amp, int& guard, int& bad) {
     float sE, cE, resid;
     const float E = kepler_f32<ITERS>(M, e, iters, sE, cE, resid);
     const float dd = fmaf(-e, cE, 1.0f);
-    if (dd * dd * guard_amp < rome2) {
+    if (GUARD && dd * dd * guard_amp < rome2) {
         double E64 = (double)E, s64, c64;
         const double e64 = (double)e;
         kepler_refine_f64(M64, e64, E64, s64, c64);
@@ -199,7 +202,7 @@ RVMC_HD float kepler_shape_f32(float M, double M64, bool neg, float e, float rom
 
 // Full single-epoch orbital RV of one sampled orbit [km/s]; the sign of the phase folds M into
 // [0, pi].
-template <int ITERS = 0>
+template <int ITERS = 0, bool GUARD = true>
 RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float* K_out, int& guard,
                            int& bad) {
     const float K = semi_amplitude_f32(P, o);
@@ -207,7 +210,7 @@ RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float*
     float sw, cw;
     sincos_turn(o.wturn, sw, cw);
     const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
-    const float shape = kepler_shape_f32<ITERS>(6.283185307179586f * aphase, RVMC_TWO_PI * (double)aphase,
+    const float shape = kepler_shape_f32<ITERS, GUARD>(6.283185307179586f * aphase, RVMC_TWO_PI * (double)aphase,
                                          o.phase < 0.0f, o.e, rome2, sw, cw, iters, P.guard_amp, guard, bad);
     if (K_out) *K_out = K;
     return K * shape;

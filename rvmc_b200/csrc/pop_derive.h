@@ -61,6 +61,17 @@ inline int derive_pop(const rvmc_pop_params& p, PopT<T>& d) {
     return 0;
 }
 
+// Can the fp64 guard of kepler_shape_f32 ever engage for this population?  The amplification
+// sqrt(1-e^2)/(1-e cos E)^2 is largest at E = 0 and grows with e, and sampled eccentricities never
+// leave [e_min, max(e_max_mid, e_max_long)] (1 % margin for the fp32 evaluation).
+inline bool guard_reachable(const rvmc_pop_params& p) {
+    double e = fmax(fmax(p.e_max_mid, p.e_max_long), p.e_min);
+    if (!(e < 1.0)) return true;
+    const double amp = sqrt(1.0 - e * e) / ((1.0 - e) * (1.0 - e));
+    const double thr = p.guard_amp > 0 ? p.guard_amp : 64.0;
+    return amp * 1.01 >= thr;
+}
+
 inline void pop_defaults(rvmc_pop_params* p) {
     p->min_mass = 6.0;
     p->max_mass = 20.0;

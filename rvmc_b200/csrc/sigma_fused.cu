@@ -61,7 +61,8 @@ __device__ __forceinline__ float slot_scale(float sigma_dyn, float err) {
 //         bank: no staging, no registers spent on it, pre-expanded Philox keys); otherwise one
 //         descriptor per grid point, staged in shared memory.
 // ITERS : Halley steps as a compile-time constant (0 = run-time kepler_iters).
-template <bool SINGLE, int ITERS>
+// GUARD : keep the fp64 guard path of the Kepler solve (false when proven unreachable on the host).
+template <bool SINGLE, int ITERS, bool GUARD>
 __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
         const u32x4 wb = draw(slot, RVMC_STREAM_ORBIT_B);
         const OrbitF32 o = sample_orbit_f32(pt.pop, wa, wb);
         int g, b;
-        const float rv = orbit_rv_f32<ITERS>(pt.pop, o, pt.kepler_iters, nullptr, g, b);
+        const float rv = orbit_rv_f32<ITERS, GUARD>(pt.pop, o, pt.kepler_iters, nullptr, g, b);
         v[l] += rv;
         my_guard += g;
         my_bad += b;
@@ -484,7 +485,7 @@ static int fused_tile_shape(int S, TileShape* ts) {
 
 static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, int64_t n_points, const float* meas_err, int S, int weighted,
                         int ddof, uint64_t first_real, int64_t n_real, float* sigma_out, int64_t sigma_stride,
-                        uint64_t* counters, bool iters1, cudaStream_t stream) {
+                        uint64_t* counters, bool iters1, bool guard, cudaStream_t stream) {
     TileShape ts;
     int rc = fused_tile_shape(S, &ts);
     if (rc) return rc;
@@ -521,8 +522,9 @@ static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, in
         RVMC_LAUNCH_CHECK();
         return RVMC_OK;
     };
-    if (single) return single->kepler_iters == 1 ? go(sigma1d_fused_kernel<true, 1>) : go(sigma1d_fused_kernel<true, 0>);
-    return iters1 ? go(sigma1d_fused_kernel<false, 1>) : go(sigma1d_fused_kernel<false, 0>);
+    const bool fast = (single ? single->kepler_iters == 1 : iters1) && !guard;
+    if (single) return fast ? go(sigma1d_fused_kernel<true, 1, false>) : go(sigma1d_fused_kernel<true, 0, true>);
+    return fast ? go(sigma1d_fused_kernel<false, 1, false>) : go(sigma1d_fused_kernel<false, 0, true>);
 }
 
 }  // namespace rvmc
@@ -552,7 +554,7 @@ int rvmc_sigma1d_fused(const rvmc_pop_params* p, uint64_t seed, const float* mea
     for (int64_t done = 0; done < n_real; done += max_real) {
         const int64_t chunk = (n_real - done < max_real) ? n_real - done : max_real;
         rc = launch_fused(&fp, nullptr, 1, meas_err, sample_size, weighted, ddof, first_real + done, chunk,
-                          sigma_out + done, 0, counters, false, stream);
+                          sigma_out + done, 0, counters, false, guard_reachable(*p), stream);
         if (rc) return rc;
     }
     return RVMC_OK;
@@ -603,11 +605,12 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     cudaStream_t stream = (cudaStream_t)cuda_stream;
 
     std::vector<FusedPoint> host(n_points);
-    bool iters1 = true;
+    bool iters1 = true, guard = false;
     for (int64_t i = 0; i < n_points; ++i) {
         rc = make_fused_point(points[i].pop, points[i].seed, &host[i]);
         if (rc) return rc;
         iters1 = iters1 && host[i].kepler_iters == 1;
+        guard = guard || guard_reachable(points[i].pop);
     }
     // stream-ordered scratch for the descriptors: no library-global state, so concurrent calls on
     // different streams do not interact
@@ -644,7 +647,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         if (!sigma_out && nb >= 2) rc = cuda_status(cudaStreamWaitEvent(stream, ev_stats[half], 0), "cudaStreamWaitEvent");
         if (rc) break;
         rc = launch_fused(nullptr, d_points + p0, np, meas_err, sample_size, weighted, ddof, 0, n_real, sig, n_real,
-                          counters, iters1, stream);
+                          counters, iters1, guard, stream);
         if (rc) break;
         rc = cuda_status(cudaEventRecord(ev_fused, stream), "cudaEventRecord");
         if (!rc) rc = cuda_status(cudaStreamWaitEvent(side, ev_fused, 0), "cudaStreamWaitEvent");

@@ -156,6 +156,34 @@ def test_fused_sigma_equals_dispersion_of_its_own_slots(S, weighted, ddof, fbin,
         np.testing.assert_allclose(got[keep], wo[keep], rtol=5e-5, atol=5e-4)
 
 
+def test_fused_guard_path_with_extreme_eccentricities():
+    """With eccentricity bounds beyond the reference's 0.9 the fp64 guard of the Kepler solve becomes
+    reachable: the guard-enabled kernel variant is selected, engages, and the per-orbit RVs keep the
+    1e-5 bound (checked against an exact fp64 solve of the same draws)."""
+    p = _abi.PopParams.defaults(e_max_long=0.985, e_power=3.0)       # e piles up near e_max
+    S, n_real, seed = 12, 4000, 99
+    out = g.empty((n_real,), "float32")
+    cnt = g.zeros((4,), "int64")
+    errd = g.up(M17, "float32")
+    g.ok(g.lib().rvmc_sigma1d_fused(C.byref(p), seed, dv.ptr(errd), S, 0, 1, 0, n_real, dv.ptr(out), dv.ptr(cnt),
+                                    g.stream()))
+    c = g.host(cnt)
+    assert c[1] > 0 and c[2] == 0                                    # guard lanes, no non-converged lanes
+    tr = _trace(p, seed, M17, S, 0, n_real * S)
+    v = (tr["noise"].astype(np.float64) + np.where(tr["is_binary"] > 0, tr["rv"].astype(np.float64), 0.0))
+    np.testing.assert_allclose(g.host(out), orc.sigma1d_unweighted(v.reshape(n_real, S), ddof=1), rtol=2e-5, atol=2e-5)
+    # exact reference values for the traced orbits
+    e = tr["e"].astype(np.float64)
+    M = 2 * np.pi * tr["uphase"].astype(np.float64)
+    E = orc.kepler_exact(M, e)
+    om = 2 * np.pi * tr["wturn"].astype(np.float64)
+    d = 1 - e * np.cos(E)
+    shape = (np.cos(E) - e) / d * np.cos(om) - np.sqrt(1 - e * e) * np.sin(E) / d * np.sin(om) + e * np.cos(om)
+    K = tr["K"].astype(np.float64)
+    assert e.max() > 0.97
+    assert np.max(np.abs(tr["rv"] - K * shape) / np.maximum(K, 1e-30)) < 1e-5
+
+
 def test_fused_sigma_is_partition_invariant():
     """Counter = global slot index: any split of the realizations gives bit-identical results."""
     p = _abi.PopParams.defaults()
