@@ -61,10 +61,12 @@ def _as_points(pops, seeds):
         if seeds is not None:
             a["seed"] = np.asarray(seeds, dtype=np.uint64)
         return a
-    a = np.empty(len(pops), dtype=POINT_DTYPE)
-    raw = a.view(np.uint8).reshape(len(pops), POINT_DTYPE.itemsize)
-    for i, p in enumerate(pops):
-        raw[i, :C.sizeof(_abi.PopParams)] = np.frombuffer(bytes(p), dtype=np.uint8)
+    n = len(pops)
+    a = np.empty(n, dtype=POINT_DTYPE)
+    if n:
+        packed = (_abi.PopParams * n)(*pops)                      # one contiguous ctypes array
+        raw = np.frombuffer(packed, dtype=np.uint8).reshape(n, C.sizeof(_abi.PopParams))
+        a.view(np.uint8).reshape(n, POINT_DTYPE.itemsize)[:, :C.sizeof(_abi.PopParams)] = raw
     a["seed"] = np.asarray(seeds, dtype=np.uint64)
     return a
 

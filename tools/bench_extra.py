@@ -79,8 +79,9 @@ def main():
     # C5: grid points per second (sigma + on-device statistics), 1e5 realizations per point
     npts = 8192 // scale
     pi = np.linspace(-0.95, 0.5, 8)
-    pops = [P(period_pi=float(pi[i % 8]), mass_ratio_kappa=-0.95 + 1.95 * ((i // 8) % 8) / 7.0,
-              fbin=0.0625 + 0.9375 * ((i // 64) % 16) / 15.0) for i in range(npts)]
+    idx = np.arange(npts)
+    pops = grid.points_array(npts, period_pi=pi[idx % 8], mass_ratio_kappa=-0.95 + 1.95 * ((idx // 8) % 8) / 7.0,
+                             fbin=0.0625 + 0.9375 * ((idx // 64) % 16) / 15.0)
     seeds = grid.point_seeds(3, npts)
 
     def run_grid():
