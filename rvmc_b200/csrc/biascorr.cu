@@ -81,11 +81,14 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
 }
 
 // NE    : compile-time bound on the epochs per star (<= 16: epoch loop fully unrolled, RVs in registers)
-// ITERS : Halley steps after the starter as a compile-time constant (0 = run-time a.kepler_iters)
-// LEAN  : the headline configuration -- measurement errors given, per-epoch RVs not written --
-//         with those two run-time switches resolved at compile time
-// GUARD : keep the fp64 guard path (false when the host has proven it unreachable)
-template <int NE, int ITERS, bool LEAN, bool GUARD>
+// FAST  : the headline configuration with every launch-uniform switch resolved at compile time --
+//         measurement errors given, per-epoch RVs not written, one Halley step, fp64 guard proven
+//         unreachable by the host (guard_reachable()), phase convention QUIRK.  !FAST keeps all of
+//         them as run-time values (same arithmetic, ~15 % more instructions).
+// Each thread walks BC_SPT samples of its star, so the per-block prologue (epoch tables, pair
+// thresholds, two barriers) is amortised over BC_THREADS * BC_SPT binaries.
+#define BC_SPT 2
+template <int NE, bool FAST, bool QUIRK>
 __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     __shared__ double A_s[NE];            // 2 pi t_obs (quirk) or t_obs (physical)
     __shared__ float err_s[NE];
@@ -93,15 +96,17 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     __shared__ int uniform_s;
     __shared__ unsigned int c_det, c_guard, c_bad;
 
+    constexpr int ITERS = FAST ? 1 : 0;
+    constexpr bool GUARD = !FAST;
     const int star = a.star0 + (int)blockIdx.y;
-    const int64_t i = (int64_t)blockIdx.x * BC_THREADS + threadIdx.x;
     const int ne = a.n_epochs[star];
-    const bool noisy = LEAN ? true : (a.rv_err != nullptr);
-    float* const rv_out = LEAN ? nullptr : a.rv_out;
+    const bool noisy = FAST ? true : (a.rv_err != nullptr);
+    const bool quirk = FAST ? QUIRK : (a.quirk_phase != 0);
+    float* const rv_out = FAST ? nullptr : a.rv_out;
 
     if (threadIdx.x < ne) {
         const double t = a.t_obs[(size_t)star * a.max_epochs + threadIdx.x];
-        A_s[threadIdx.x] = a.quirk_phase ? RVMC_TWO_PI * t : t;
+        A_s[threadIdx.x] = quirk ? RVMC_TWO_PI * t : t;
         err_s[threadIdx.x] = noisy ? a.rv_err[(size_t)star * a.max_epochs + threadIdx.x] : 0.0f;
     }
     if (threadIdx.x == 0) {
@@ -124,10 +129,12 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
     }
     __syncthreads();
 
-    const bool valid = i < a.n_samples;
-    unsigned int my_guard = 0, my_bad = 0;
-    bool det = false;
-    if (valid) {
+    unsigned int my_guard = 0, my_bad = 0, my_det = 0;
+    const int64_t i_first = (int64_t)blockIdx.x * (BC_THREADS * BC_SPT) + threadIdx.x;
+#pragma unroll 1
+    for (int rep = 0; rep < BC_SPT; ++rep) {
+        const int64_t i = i_first + (int64_t)rep * BC_THREADS;
+        if (i >= a.n_samples) break;
         const uint64_t sample = a.first_sample + (uint64_t)i;
         const uint64_t item = bc_item(a.first_star + star, sample);
         const u32x4 wa = philox_block(a.key, item, RVMC_STREAM_ORBIT_A, 0);
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
         // 1/P is ever needed: time = u P (RVMC_bias_corr.py:328), so t / P = t_obs / P + u, and the
         // eccentricity regimes compare log10 P.
         const double xd = powerlaw_f64(a.P64.logp, u01_f64(wa.y));
-        const double invP = exp10(-4.9365137424788932 - xd);            // 1 / (86400 * 10^x)  [1/s]
+        const double invP = exp10_fast_f64(-4.9365137424788932 - xd);   // 1 / (86400 * 10^x)  [1/s]
         o.x = (float)xd;
         const double uphase = u01_f64(wa.z);
         o.q = powerlaw_f32(a.P32.q, u01_f32(wa.w));
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
         float sw, cw;
         sincos_turn(o.wturn, sw, cw);
         const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
-        const double c0 = a.quirk_phase ? RVMC_TWO_PI * uphase : uphase;
+        const double c0 = quirk ? RVMC_TWO_PI * uphase : uphase;
 
         // ---- epochs -----------------------------------------------------------------------------
         float rvs[NE];
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
             // [0,1) and used as radians; physical: 2 pi frac(t_obs / P + u)
             const double v = fma(A_s[k], invP, c0);
             const double fr = v - floor(v);
-            if (a.quirk_phase) {
+            if (quirk) {
                 M64 = fr;
             } else {
                 const double fold = fr - rint(fr);                  // [-0.5, 0.5]
@@ -200,10 +207,16 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
             if (rv_out) rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
         };
         if constexpr (NE <= 16) {
-            // fully unrolled: rvs[] and z[] live in registers
+            // fully unrolled: rvs[] and z[] live in registers; a star with exactly NE epochs (the common
+            // case: NE is chosen from max_epochs) takes the branch-free copy
+            if (ne == NE) {
 #pragma unroll
-            for (int k = 0; k < NE; ++k)
-                if (k < ne) epoch(k);
+                for (int k = 0; k < NE; ++k) epoch(k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NE; ++k)
+                    if (k < ne) epoch(k);
+            }
         } else {
 #pragma unroll 1
             for (int k = 0; k < ne; ++k) epoch(k);
@@ -214,6 +227,7 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
         if (a.delta_rv) a.delta_rv[(size_t)star * a.sample_stride + i] = drv;
 
         // ---- significance test --------------------------------------------------------------------
+        bool det = false;
         if (noisy) {
             if (uniform_s) {
                 // equal errors: every pair has the same threshold, so the largest difference decides
@@ -230,34 +244,37 @@ __global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
             }
         }
         if (a.detected) a.detected[(size_t)star * a.sample_stride + i] = det ? 1 : 0;
+        my_det += det ? 1u : 0u;
     }
 
     // ---- counters ---------------------------------------------------------------------------------
-    const unsigned int ballot = __ballot_sync(0xffffffffu, det);
-    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&c_det, (unsigned int)__popc(ballot));
-    if (my_guard) atomicAdd(&c_guard, my_guard);
-    if (my_bad) atomicAdd(&c_bad, my_bad);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int64_t first = (int64_t)blockIdx.x * BC_THREADS;
-        const int64_t nvalid = min((int64_t)BC_THREADS, a.n_samples - first);
-        if (a.counters) {
-            atomicAdd(a.counters + 0, (unsigned long long)(nvalid * ne));
-            if (c_det) atomicAdd(a.counters + 1, (unsigned long long)c_det);
-            if (c_guard) atomicAdd(a.counters + 2, (unsigned long long)c_guard);
-            if (c_bad) atomicAdd(a.counters + 3, (unsigned long long)c_bad);
+    if (a.counters || a.det_per_star) {
+        for (int off = 16; off > 0; off >>= 1) my_det += __shfl_xor_sync(0xffffffffu, my_det, off);
+        if ((threadIdx.x & 31) == 0 && my_det) atomicAdd(&c_det, my_det);
+        if (my_guard) atomicAdd(&c_guard, my_guard);
+        if (my_bad) atomicAdd(&c_bad, my_bad);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int64_t first = (int64_t)blockIdx.x * (BC_THREADS * BC_SPT);
+            const int64_t nvalid = min((int64_t)(BC_THREADS * BC_SPT), a.n_samples - first);
+            if (a.counters) {
+                atomicAdd(a.counters + 0, (unsigned long long)(nvalid * ne));
+                if (c_det) atomicAdd(a.counters + 1, (unsigned long long)c_det);
+                if (c_guard) atomicAdd(a.counters + 2, (unsigned long long)c_guard);
+                if (c_bad) atomicAdd(a.counters + 3, (unsigned long long)c_bad);
+            }
+            if (a.det_per_star && c_det) atomicAdd(a.det_per_star + star, c_det);
         }
-        if (a.det_per_star && c_det) atomicAdd(a.det_per_star + star, c_det);
     }
 }
 
-template <int NE, int ITERS, bool LEAN, bool GUARD>
+template <int NE, bool FAST, bool QUIRK>
 static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
     // gridDim.y carries the star (<= 65535 per launch)
     for (int s0 = 0; s0 < a.nstars; s0 += 65535) {
         a.star0 = s0;
         const int ny = a.nstars - s0 < 65535 ? a.nstars - s0 : 65535;
-        biascorr_fused_kernel<NE, ITERS, LEAN, GUARD>
+        biascorr_fused_kernel<NE, FAST, QUIRK>
             <<<dim3((unsigned int)blocks_per_star, (unsigned int)ny), BC_THREADS, 0, stream>>>(a);
         RVMC_LAUNCH_CHECK();
     }
@@ -266,20 +283,13 @@ static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
 
 template <int NE>
 static int bc_dispatch(BcArgs& a, bool guard, int64_t blocks_per_star, cudaStream_t stream) {
-    const bool lean = a.rv_err != nullptr && a.rv_out == nullptr;
     if constexpr (NE <= 8) {
-        if (a.kepler_iters == 1) {
-            if (!guard)
-                return lean ? bc_launch<NE, 1, true, false>(a, blocks_per_star, stream)
-                            : bc_launch<NE, 1, false, false>(a, blocks_per_star, stream);
-            return lean ? bc_launch<NE, 1, true, true>(a, blocks_per_star, stream)
-                        : bc_launch<NE, 1, false, true>(a, blocks_per_star, stream);
-        }
-        return lean ? bc_launch<NE, 0, true, true>(a, blocks_per_star, stream)
-                    : bc_launch<NE, 0, false, true>(a, blocks_per_star, stream);
-    } else {
-        return bc_launch<NE, 0, false, true>(a, blocks_per_star, stream);
+        const bool fast = a.rv_err != nullptr && a.rv_out == nullptr && a.kepler_iters == 1 && !guard;
+        if (fast)
+            return a.quirk_phase ? bc_launch<NE, true, true>(a, blocks_per_star, stream)
+                                 : bc_launch<NE, true, false>(a, blocks_per_star, stream);
     }
+    return bc_launch<NE, false, false>(a, blocks_per_star, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -501,7 +511,7 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
     a.rv_out = rv_out;
     a.counters = (unsigned long long*)counters;
     a.det_per_star = det_per_star;
-    const int64_t blocks_per_star = (n_samples + BC_THREADS - 1) / BC_THREADS;
+    const int64_t blocks_per_star = (n_samples + BC_THREADS * BC_SPT - 1) / (BC_THREADS * BC_SPT);
     if (blocks_per_star > 0x7fffffffLL) {
         set_error("too many samples in one launch (%lld); shard them", (long long)n_samples);
         return RVMC_ERR_UNSUPPORTED;

@@ -137,6 +137,32 @@ RVMC_HD void sincos_f64_bounded(double x, double& s, double& c) {
     c = ((q + 1) & 2) ? -b : b;
 }
 
+// 10^y in fp64 for moderate |y| (|y| < ~300), relative error < 5e-14: y log2(10) = n + f with
+// |f| <= 0.5, 2^f by an 11th-degree Taylor polynomial in f ln 2, scaled by 2^n through the exponent
+// field.  ~18 instructions against ~50 for exp10(): the multi-epoch kernel needs 1/P to ~1e-10.
+RVMC_HD double exp10_fast_f64(double y) {
+    const double t = y * 3.3219280948873623479;           // log2(10)
+    const double n = rint(t);
+    const double g = (t - n) * 0.69314718055994530942;    // f ln 2, |g| <= 0.3466
+    double p = 2.50521083854417187751e-08;                // 1/11!
+    p = fma(p, g, 2.75573192239858906526e-07);            // 1/10!
+    p = fma(p, g, 2.75573192239858906526e-06);            // 1/9!
+    p = fma(p, g, 2.48015873015873015873e-05);            // 1/8!
+    p = fma(p, g, 1.98412698412698412698e-04);            // 1/7!
+    p = fma(p, g, 1.38888888888888888889e-03);            // 1/6!
+    p = fma(p, g, 8.33333333333333333333e-03);            // 1/5!
+    p = fma(p, g, 4.16666666666666666667e-02);            // 1/4!
+    p = fma(p, g, 1.66666666666666666667e-01);            // 1/3!
+    p = fma(p, g, 0.5);
+    p = fma(p, g, 1.0);
+    p = fma(p, g, 1.0);
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
+#else
+    return ldexp(p, (int)n);
+#endif
+}
+
 // ---- normals ---------------------------------------------------------------------------------
 // Box-Muller from two Philox words: z0 = r cos(theta), z1 = r sin(theta); replaces
 // np.random.normal (legacy polar method) at every noise site of the reference.

@@ -106,6 +106,10 @@ void hc_box_muller(int64_t n, const uint32_t* w1, const uint32_t* w2, float* z0,
     }
 }
 
+void hc_exp10_fast(int64_t n, const double* y, double* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = exp10_fast_f64(y[i]);
+}
+
 void hc_sincos_f64(int64_t n, const double* x, double* s, double* c) {
     for (int64_t i = 0; i < n; ++i) sincos_f64_bounded(x[i], s[i], c[i]);
 }

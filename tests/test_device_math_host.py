@@ -177,6 +177,14 @@ def test_box_muller_and_sincos():
     assert np.max(np.abs(c - np.cos(x.astype(np.float64)))) < 2e-7
 
 
+def test_exp10_fast_f64():
+    lib = load_hostcheck()
+    y = np.concatenate([np.linspace(-12, 6, 200001), [0.0, -4.9365137424788932 - 0.15, -4.9365137424788932 - 3.5]])
+    out = np.empty_like(y)
+    lib.hc_exp10_fast(C.c_int64(y.size), y.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.max(np.abs(out / 10.0 ** y - 1)) < 5e-14
+
+
 def test_sincos_f64_bounded():
     lib = load_hostcheck()
     rng = np.random.RandomState(11)
