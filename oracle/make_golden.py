@@ -201,6 +201,38 @@ def golden_distributions(ref_rvmc, ref_bc, name="reference_distributions"):
     print(name, {k: (float(np.median(v)) if v.ndim else float(v)) for k, v in out.items() if k.startswith(("sigma_f", "biascorr_det"))})
 
 
+def golden_grid_surface(ref_rvmc, name="reference_grid_surface"):
+    """The reference's own grid-fit semantics (findBestDistributions.py:21-32,40,78,47-60) evaluated
+    with the UNMODIFIED RVMC class standing in for the missing `main_RVMC.synthetic_RV_distribution`
+    (SURVEY.md 8c): for each (P_min, f_bin) cell a 10^5-star pool, 2*10^4 bootstraps of 12 stars with
+    the M17 errors, np.std with ddof=0, and the statistics of :47-60."""
+    np.random.seed(424242)
+    periods = np.logspace(np.log10(1.4), np.log10(3500), 8)
+    fbins = np.linspace(0.1, 1.0, 6)
+    keys = ("mode", "mean", "median", "p05", "p16", "p84", "p95")
+    surf = {k: np.zeros((len(fbins), len(periods))) for k in keys}
+    for a, fbin in enumerate(fbins):
+        for b, pmin in enumerate(periods):
+            c = ref_rvmc.RVMC(number_of_stars=10 ** 5, min_mass=6, max_mass=20, fbin=fbin, min_period=pmin,
+                              max_period=3500, sigma_dyn=2.0)
+            c.calculate_binary_velocities()
+            c.calculate_radial_velocity()
+            rv_dist = c.radial_velocities
+            sig1D = np.std(np.random.choice(rv_dist, (20000, 12)) + np.random.normal(0, M17_ERRORS, (20000, 12)),
+                           axis=1)                                                    # ddof = 0 (:29-30)
+            bins = np.arange(0, max(sig1D) + 0.5, 0.5)
+            values, bins = np.histogram(sig1D, bins=bins, density=True)
+            index = int(np.where(values == np.max(values))[0][0])
+            surf["mode"][a, b] = bins[index] + (bins[1] - bins[0]) / 2.
+            surf["mean"][a, b] = np.mean(sig1D)
+            surf["median"][a, b] = np.median(sig1D)
+            for q, k in ((5, "p05"), (16, "p16"), (84, "p84"), (95, "p95")):
+                surf[k][a, b] = np.percentile(sig1D, q)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), periods=periods, fbins=fbins, m17_errors=M17_ERRORS,
+                        n_real=20000, **surf)
+    print(name, "median surface corners:", surf["median"][0, 0], surf["median"][-1, 0], surf["median"][-1, -1])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_rvmc, ref_bc = _import_reference()
@@ -216,6 +248,7 @@ def main():
     golden_biascorr(ref_bc, "biascorr_masses_ragged", seed=5, nsamples=192, mode="masses")
     golden_biascorr(ref_bc, "biascorr_imf_6epochs", seed=9, nsamples=256, mode="imf")
     golden_distributions(ref_rvmc, ref_bc)
+    golden_grid_surface(ref_rvmc)
 
 
 if __name__ == "__main__":

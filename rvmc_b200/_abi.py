@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librvmc_b200.so")
+# RVMC_B200_LIB lets a developer point at an experimental build of the same ABI (tuning sweeps)
+LIB_PATH = os.environ.get("RVMC_B200_LIB") or os.path.join(HERE, "librvmc_b200.so")
 
 RVMC_OK = 0
 RVMC_ERR_INVALID = -1

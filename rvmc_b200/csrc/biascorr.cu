@@ -87,9 +87,14 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
 //         them as run-time values (same arithmetic, ~15 % more instructions).
 // Each thread walks BC_SPT samples of its star, so the per-block prologue (epoch tables, pair
 // thresholds, two barriers) is amortised over BC_THREADS * BC_SPT binaries.
+#ifndef BC_SPT
 #define BC_SPT 2
+#endif
+#ifndef BC_MIN_BLOCKS
+#define BC_MIN_BLOCKS 1
+#endif
 template <int NE, bool FAST, bool QUIRK>
-__global__ void __launch_bounds__(BC_THREADS) biascorr_fused_kernel(BcArgs a) {
+__global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kernel(BcArgs a) {
     __shared__ double A_s[NE];            // 2 pi t_obs (quirk) or t_obs (physical)
     __shared__ float err_s[NE];
     __shared__ float thr_s[NE * NE];      // pair thresholds max(delta_RV, n_sigma sqrt(ea^2+eb^2))

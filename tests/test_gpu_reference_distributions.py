@@ -57,3 +57,33 @@ def test_delta_rv_and_detection_vs_reference(ref):
         p_ref = float(ref["biascorr_detected_fraction"][i])
         se = np.sqrt(p_ref * (1 - p_ref) * (1 / 20000 + 1 / 200000))
         assert abs(det[i].mean() - p_ref) < 4 * se, (i, det[i].mean(), p_ref)
+
+
+def test_grid_surface_and_best_fit_vs_reference_grid():
+    """The reference's grid-fit semantics run with its own RVMC class (tests/golden/
+    reference_grid_surface.npz) vs rvmc_grid_run: statistic surfaces agree within the reference's
+    pool + Monte-Carlo noise, and the best-fit cell for an observed sigma lands within one cell
+    (neighbouring cells differ by less than the reference's own noise)."""
+    from rvmc_b200 import grid
+    z, _ = g.golden("reference_grid_surface")
+    periods, fbins = z["periods"], z["fbins"]
+    F, P = np.meshgrid(fbins, periods, indexing="ij")
+    pops = grid.points_array(F.size, fbin=F.ravel(), min_period=P.ravel(), max_period=3500.0, min_mass=6.0,
+                             max_mass=20.0, sigma_dyn=2.0)
+    res = grid.run_points(pops, grid.point_seeds(17, F.size), z["m17_errors"], 12, 100000, bin=0.5, ddof=0,
+                          distributed=False)
+    st = res["stats"].reshape(F.shape)
+    for k, tol in (("median", 0.04), ("mean", 0.04), ("p16", 0.05), ("p84", 0.05), ("p05", 0.07), ("p95", 0.07)):
+        rel = np.abs(st[k] / z[k] - 1)
+        assert rel.max() < tol, (k, rel.max())
+    assert np.median(np.abs(st["median"] / z["median"] - 1)) < 0.01
+    assert np.max(np.abs(st["mode"] - z["mode"])) <= 2.5             # 0.5 km/s bins, flat-topped histograms
+    # best fit along the P_min axis for each binary fraction, observed sigma = the reference's median
+    for a in range(len(fbins)):
+        ours = {k: list(st[k][a]) for k in ("mode", "median", "p05", "p16", "p84", "p95")}
+        for j in (1, 3, 5):
+            obs = float(z["median"][a, j])
+            row = grid.find_best_Pmin(obs, 6, 20, 12, ours["mode"], ours["median"], ours["p05"], ours["p16"],
+                                      ours["p84"], ours["p95"], None, None, list(periods), write=False)
+            jj = int(np.argmin(np.abs(periods - row[0])))
+            assert abs(jj - j) <= 1, (a, j, jj)
