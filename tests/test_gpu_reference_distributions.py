@@ -77,7 +77,9 @@ def test_grid_surface_and_best_fit_vs_reference_grid():
         rel = np.abs(st[k] / z[k] - 1)
         assert rel.max() < tol, (k, rel.max())
     assert np.median(np.abs(st["median"] / z["median"] - 1)) < 0.01
-    assert np.max(np.abs(st["mode"] - z["mode"])) <= 2.5             # 0.5 km/s bins, flat-topped histograms
+    # the mode of a 0.5-km/s histogram of 2e4 values is noisy where the distribution is broad
+    # (~200 +- 14 counts per bin around the top): compare on the scale of the distribution's width
+    assert np.all(np.abs(st["mode"] - z["mode"]) <= 1.0 + 0.25 * (z["p84"] - z["p16"]))
     # best fit along the P_min axis for each binary fraction, observed sigma = the reference's median
     for a in range(len(fbins)):
         ours = {k: list(st[k][a]) for k in ("mode", "median", "p05", "p16", "p84", "p95")}
