@@ -44,10 +44,12 @@ def points_array(n, **columns):
     """Record array of n grid points filled with the reference defaults (RVMC.py:28-43), then the
     given columns (scalars or length-n arrays of any rvmc_pop_params field, or `seed`)."""
     d = _abi.PopParams.defaults()
-    a = np.empty(int(n), dtype=POINT_DTYPE)
+    one = np.zeros(1, dtype=POINT_DTYPE)
     for f in POP_FIELDS:
-        a[f] = getattr(d, f)
-    a["kepler_iters"], a["reserved"], a["seed"] = d.kepler_iters, 0, 0
+        one[f] = getattr(d, f)
+    one["kepler_iters"] = d.kepler_iters
+    a = np.empty(int(n), dtype=POINT_DTYPE)
+    a[:] = one[0]                                   # one broadcast of the default record
     for k, v in columns.items():
         if k not in POINT_DTYPE.names:
             raise TypeError("unknown population parameter %r" % k)
@@ -122,14 +124,14 @@ def point_seeds(seed, n_points, common_random_numbers=False):
     most of the point-to-point noise from the statistic surfaces."""
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     if common_random_numbers:
-        return [seed] * n_points
+        return np.full(n_points, seed, dtype=np.uint64)
     with np.errstate(over="ignore"):
         x = np.uint64(seed) + np.uint64(0x632BE59BD9B4E019) * np.arange(1, n_points + 1, dtype=np.uint64)
         x = x + np.uint64(0x9E3779B97F4A7C15)                       # splitmix64, vectorised (wraps mod 2^64)
         z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
-    return [int(v) for v in z]
+    return z
 
 
 def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**5, bin=0.5, ddof=0,
@@ -158,7 +160,7 @@ def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**
     t = dv.torch()
     ns = int(number_of_samples)
     nl = len(local)
-    pts_np = np.ascontiguousarray(all_pts[local]) if nl else np.zeros(1, dtype=POINT_DTYPE)
+    pts_np = np.ascontiguousarray(all_pts[rank::world]) if nl else np.zeros(1, dtype=POINT_DTYPE)
     pts = pts_np.ctypes.data_as(C.POINTER(_abi.GridPoint))
     stats_d = dv.zeros((max(nl, 1) * STATS_DTYPE.itemsize,), "uint8", dev)
     errd = dv.to_device(err, "float32", dev)

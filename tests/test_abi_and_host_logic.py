@@ -138,7 +138,10 @@ def test_best_fit_rule_and_seeds_and_shards():
     far = [500.0] * 4
     assert grid.best_fit_indices(10.0, far, far, far, far, far, far) == (0, 0, 0, 0, 0)    # nothing within 100
     s = grid.point_seeds(1, 1000)
-    assert len(set(s)) == 1000 and grid.point_seeds(1, 3, True) == [1, 1, 1] and s == grid.point_seeds(1, 1000)
+    assert s.dtype == np.uint64 and len(set(s.tolist())) == 1000 and grid.point_seeds(1, 3, True).tolist() == [1, 1, 1]
+    assert np.array_equal(s, grid.point_seeds(1, 1000))
+    from rvmc_b200._device import splitmix64
+    assert int(s[4]) == splitmix64((1 + 0x632BE59BD9B4E019 * 5) & 0xFFFFFFFFFFFFFFFF)
     for n, w in ((65536, 8), (10, 4), (3, 8), (0, 2)):
         parts = [grid.shard_indices(n, r, w) for r in range(w)]
         assert sorted(np.concatenate(parts).tolist()) == list(range(n))

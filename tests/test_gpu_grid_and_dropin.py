@@ -42,7 +42,7 @@ def test_grid_stats_match_numpy_rules_on_the_same_sigmas(n_real, S):
         assert res["hist"][i][len(cnt):].sum() == 0
     # the same points one by one through the single-population entry give the same sigmas
     out = g.empty((n_real,), "float32")
-    g.ok(g.lib().rvmc_sigma1d_fused(C.byref(pops[4]), seeds[4], dv.ptr(g.up(np.resize(M17, S), "float32")), S, 0, 0, 0,
+    g.ok(g.lib().rvmc_sigma1d_fused(C.byref(pops[4]), int(seeds[4]), dv.ptr(g.up(np.resize(M17, S), "float32")), S, 0, 0, 0,
                                     n_real, dv.ptr(out), None, g.stream()))
     np.testing.assert_array_equal(g.host(out), res["sigma"][4])
 
