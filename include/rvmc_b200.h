@@ -177,7 +177,8 @@ RVMC_API int rvmc_mix_pool(uint64_t seed, uint32_t call_id, int64_t n, double fb
 /* ---- a16: finite-pool bootstrap (RVMC.subsample, RVMC.py:262-271) ---------------------------
  * sigma_out[r] for realizations [first_real, first_real+n_real): sample_size with-replacement
  * picks from pool[pool_n] + N(0, meas_err[j]); unweighted std with `ddof` (1 for RVMC.py:271,
- * 0 for findBestDistributions.py:29) or the weighted formula of RVMC.py:263-268.
+ * 0 for findBestDistributions.py:29) or the weighted formula of RVMC.py:263-268 (ddof = 0; with
+ * ddof = 1 the Bessel-corrected variant left commented out at RVMC.py:267).
  * meas_err: device float64[sample_size]. */
 RVMC_API int rvmc_sigma1d_pool(uint64_t seed, uint32_t call_id, const double* pool, int64_t pool_n,
                       const double* meas_err, int sample_size, int weighted, int ddof,

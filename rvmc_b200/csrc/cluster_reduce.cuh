@@ -66,9 +66,12 @@ __device__ __forceinline__ void reduce_tile_sigma(const T* v, int nr, int S, int
         if (valid && gl == 0) {
             T var;
             if (wts) {
-                // sum w (v - mu)^2 / sum w  with  mu = pivot + s1 / wsum            (RVMC.py:263-268)
+                // sum w (v - mu)^2 / sum w  with  mu = pivot + s1 / wsum            (RVMC.py:263-268);
+                // ddof = 1 applies the Bessel-type factor S/(S-1) of the variant the reference keeps
+                // commented out at RVMC.py:267
                 const T m = s1 / wsum;
                 var = s2 / wsum - m * m;
+                if (ddof) var = var * (T)S / (T)(S - ddof);
             } else {
                 // S == ddof -> 0/0 = NaN like NumPy
                 var = (s2 - s1 * s1 / (T)S) / (T)(S - ddof);

@@ -289,9 +289,11 @@ class RVMC(dv.LazyArrays):
         return np.full(int(sample_size), measured_errors, dtype=np.float64)
 
     def subsample(self, sample_size=12, measured_errors=1.2, number_of_samples=10**5, fbin=None, weighted=False,
-                  materialize=True):
+                  materialize=True, bessel=False):
         """Bootstraps `number_of_samples` clusters of `sample_size` stars from the pool and returns
-        their velocity dispersions (RVMC.py:238-273; finite-pool semantics, ddof=1 or weighted)."""
+        their velocity dispersions (RVMC.py:238-273; finite-pool semantics, ddof=1 or weighted).
+        `bessel=True` (additive) applies the S/(S-1) correction the reference keeps commented
+        out at RVMC.py:267 to the weighted dispersion."""
         err = self._errors_vector(sample_size, measured_errors)
         if weighted and isinstance(measured_errors, (list, tuple)):
             # `1 / measured_errors**2` (RVMC.py:263) needs an ndarray or a float
@@ -307,19 +309,22 @@ class RVMC(dv.LazyArrays):
         errd = dv.to_device(err, "float64", dev)
         with dv.DeviceGuard(dev):
             _abi.check(_abi.lib().rvmc_sigma1d_pool(self._next_seed(), 0, dv.ptr(pool), pool.numel(), dv.ptr(errd),
-                                                    int(sample_size), int(bool(weighted)), 1, 0, ns, dv.ptr(out),
+                                                    int(sample_size), int(bool(weighted)),
+                                                    (1 if bessel else 0) if weighted else 1, 0, ns, dv.ptr(out),
                                                     dv.stream_ptr(dev)))
         self._set_device("sigma_1d", out)
         return self.sigma_1d if materialize else None
 
     def subsample_fused(self, sample_size=12, measured_errors=1.2, number_of_samples=10**5, fbin=None,
-                        weighted=False, ddof=1, first_realization=0, seed=None, return_counters=False,
+                        weighted=False, ddof=None, first_realization=0, seed=None, return_counters=False,
                         materialize=True):
         """Infinite-pool limit of `subsample()`: every star of every realization is a fresh binary
         (probability fbin) or single; sampling, Kepler solve, RV and dispersion are fused in one
         kernel and per-star values never leave the chip.  Uses the CURRENT population parameters
         (not the materialised arrays).  Returns float32 dispersions."""
         err = self._errors_vector(sample_size, measured_errors)
+        if ddof is None:
+            ddof = 0 if weighted else 1           # RVMC.py:268 (no Bessel term) / :271 (ddof=1)
         if fbin is not None:
             self.fbin = fbin
         pop = self._pop()

@@ -56,7 +56,8 @@ def test_sigma1d_pool_matches_oracle_on_same_draws(S, weighted, ddof, n_real, fi
     g.ok(g.lib().rvmc_sigma1d_pool(seed, 2, dv.ptr(g.up(pool, "float64")), len(pool), dv.ptr(g.up(err, "float64")),
                                    S, weighted, ddof, first, n_real, dv.ptr(out), g.stream()))
     rvs = pool_bootstrap_from_draws(seed, 2, pool, err, S, first, n_real)
-    want = orc.sigma1d_weighted(rvs, err) if weighted else orc.sigma1d_unweighted(rvs, ddof=ddof)
+    want = orc.sigma1d_weighted(rvs, err) * np.sqrt(S / (S - ddof)) if weighted else \
+        orc.sigma1d_unweighted(rvs, ddof=ddof)          # weighted + ddof=1: the commented variant of RVMC.py:267
     np.testing.assert_allclose(g.host(out), want, rtol=1e-11, atol=1e-12)
 
 
@@ -141,7 +142,8 @@ def test_fused_sigma_equals_dispersion_of_its_own_slots(S, weighted, ddof, fbin,
     v = (tr["noise"].astype(np.float64) + np.where(tr["is_binary"] > 0, tr["rv"].astype(np.float64), 0.0))
     v = v.reshape(n_real, S)
     with np.errstate(invalid="ignore", divide="ignore"):
-        want = orc.sigma1d_weighted(v, err) if weighted else orc.sigma1d_unweighted(v, ddof=ddof)
+        bessel = np.sqrt(S / (S - ddof)) if (weighted and S > ddof) else 1.0
+        want = orc.sigma1d_weighted(v, err) * bessel if weighted else orc.sigma1d_unweighted(v, ddof=ddof)
     if S - ddof == 0 and not weighted:
         assert np.all(np.isnan(got))
     else:
@@ -151,7 +153,7 @@ def test_fused_sigma_equals_dispersion_of_its_own_slots(S, weighted, ddof, fbin,
     if S <= 332 and S - ddof > 0:
         o = fused_slots_from_draws(p, seed, err, S, first * S, n_real * S)
         vo = o["value"].reshape(n_real, S)
-        wo = orc.sigma1d_weighted(vo, err) if weighted else orc.sigma1d_unweighted(vo, ddof=ddof)
+        wo = orc.sigma1d_weighted(vo, err) * bessel if weighted else orc.sigma1d_unweighted(vo, ddof=ddof)
         keep = ~near_regime_edge(o["orbits"]).reshape(n_real, S).any(axis=1)
         np.testing.assert_allclose(got[keep], wo[keep], rtol=5e-5, atol=5e-4)
 
