@@ -63,6 +63,8 @@ def to_device(array, dtype, device):
     if isinstance(array, t.Tensor):
         return array.to(device=device, dtype=getattr(t, dtype)).contiguous()
     a = np.ascontiguousarray(np.asarray(array), dtype=np.dtype(dtype))
+    if not a.flags.writeable:          # e.g. np.broadcast_to views: torch.from_numpy wants a writable buffer
+        a = a.copy()
     return t.from_numpy(a).to(device)
 
 
