@@ -40,13 +40,28 @@ def is_stale():
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link the shared library.  Returns its path."""
+def build(force=False, verbose=False, bounds_check=False):
+    """Compile every CUDA source for sm_100a and link the shared library.  Returns its path.
+    `bounds_check=True` builds librvmc_b200_bounds.so with device-side assertions on the shared-memory
+    indexing (-DRVMC_BOUNDS_CHECK); run it with RVMC_B200_LIB=<path> (compute-sanitizer stand-in)."""
+    global OUT, OBJ_DIR
+    if bounds_check:
+        out, obj_dir = OUT.replace(".so", "_bounds.so"), OBJ_DIR + "_bounds"
+        saved = (OUT, OBJ_DIR)
+        OUT, OBJ_DIR = out, obj_dir
+        try:
+            return _build(True, verbose, ["-DRVMC_BOUNDS_CHECK"])
+        finally:
+            OUT, OBJ_DIR = saved
     if not force and not is_stale():
         return OUT
+    return _build(force, verbose, [])
+
+
+def _build(force, verbose, defines):
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + list(defines)
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
@@ -71,5 +86,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, bounds_check="--bounds" in sys.argv)
     print(path)

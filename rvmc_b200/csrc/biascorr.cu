@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
     constexpr bool GUARD = !FAST;
     const int star = a.star0 + (int)blockIdx.y;
     const int ne = a.n_epochs[star];
+    RVMC_DEV_ASSERT(star >= 0 && star < a.nstars && ne >= 0 && ne <= NE && ne <= a.max_epochs);
     const bool noisy = FAST ? true : (a.rv_err != nullptr);
     const bool quirk = FAST ? QUIRK : (a.quirk_phase != 0);
     float* const rv_out = FAST ? nullptr : a.rv_out;

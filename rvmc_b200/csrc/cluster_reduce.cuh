@@ -14,6 +14,10 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef RVMC_DEV_ASSERT
+#define RVMC_DEV_ASSERT(cond) ((void)0)
+#endif
+
 namespace rvmc {
 
 // threads: block size; R: realizations per tile.  Smallest power of two G with R*G >= threads.
@@ -43,6 +47,7 @@ __device__ __forceinline__ void reduce_tile_sigma(const T* v, int nr, int S, int
         const int r = it * ng + gi;
         const bool valid = r < nr;
         const T* row = v + (size_t)(valid ? r : 0) * S;
+        RVMC_DEV_ASSERT(G >= 1 && G <= 32 && (G & (G - 1)) == 0 && gl < G);
         const T pivot = row[0];
         T s1 = 0, s2 = 0;
         if (wts) {

@@ -32,6 +32,15 @@ inline unsigned int grid_stride_blocks(int64_t n, int threads, int blocks_per_sm
 
 }  // namespace rvmc
 
+// Device-side bounds checks for debug builds (nvcc -DRVMC_BOUNDS_CHECK): compute-sanitizer is not
+// available on every pool, so the shared-memory indexing of the fused kernels can assert itself.
+#if defined(RVMC_BOUNDS_CHECK)
+#include <assert.h>
+#define RVMC_DEV_ASSERT(cond) assert(cond)
+#else
+#define RVMC_DEV_ASSERT(cond) ((void)0)
+#endif
+
 #define RVMC_REQUIRE(cond, ...)              \
     do {                                     \
         if (!(cond)) {                       \

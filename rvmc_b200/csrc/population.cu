@@ -7,8 +7,8 @@
 //   calculate_semi_major_axis / max_orbital_velocity / binary_radial_velocity   RVMC.py:182-212
 //   calculate_radial_velocity (pool mixing)    RVMC.py:228-236
 //   subsample (bootstrap + dispersion)         RVMC.py:238-273
-#include "cluster_reduce.cuh"
 #include "common.cuh"
+#include "cluster_reduce.cuh"
 #include "pop_derive.h"
 
 namespace rvmc {
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(256) sigma1d_pool_kernel(uint64_t seed, uint32
                     const int j = (int)l - r * S;
                     const uint32_t word = h ? w.y : w.x;
                     const uint32_t idx = (uint32_t)(((uint64_t)word * (uint64_t)pool_n) >> 32);
+                    RVMC_DEV_ASSERT(idx < pool_n && r >= 0 && r < nr && j >= 0 && j < S);
                     v[l] = pool[idx] + (h ? z1 : z0) * err[j];
                 }
             }

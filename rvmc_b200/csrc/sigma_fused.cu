@@ -21,8 +21,8 @@
 // the tile size, the launch geometry or the GPU the tile ran on.  Per-star values never reach HBM.
 #include <vector>
 
-#include "cluster_reduce.cuh"
 #include "common.cuh"
+#include "cluster_reduce.cuh"
 #include "pop_derive.h"
 
 namespace rvmc {
@@ -131,13 +131,16 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
             const int64_t la = (int64_t)(2 * pair - slot0);
             l0 = (int)la;
             l1 = l0 + 1;
+            RVMC_DEV_ASSERT(l0 >= -1 && l0 < nslots && l1 <= nslots);
             if (l0 >= 0) {          // l0 < nslots always (pair range)
                 const int r = (int)(((float)l0 + 0.5f) * invS);
+                RVMC_DEV_ASSERT(r >= 0 && r < nr && l0 - r * S >= 0 && l0 - r * S < S);
                 v[l0] = z0 * scale[l0 - r * S];
                 bin0 = (w.x >> 8) < thresh;
             }
             if (l1 < nslots) {
                 const int r = (int)(((float)l1 + 0.5f) * invS);
+                RVMC_DEV_ASSERT(r >= 0 && r < nr && l1 - r * S >= 0 && l1 - r * S < S);
                 v[l1] = z1 * scale[l1 - r * S];
                 bin1 = (w.y >> 8) < thresh;
             }
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
         if (lane == 0 && (c0 + c1)) base = atomicAdd(&qn, c0 + c1);
         base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned below = (1u << lane) - 1u;
+        RVMC_DEV_ASSERT(base >= 0 && base + c0 + c1 <= nslots);
         if (bin0) queue[base + __popc(m0 & below)] = (uint16_t)l0;
         if (bin1) queue[base + c0 + __popc(m1 & below)] = (uint16_t)l1;
     }
@@ -157,9 +161,11 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
 
     // ---- phase B: orbits of the queued binaries -------------------------------------------------
     const int nq = qn;
+    RVMC_DEV_ASSERT(nq >= 0 && nq <= nslots);
     unsigned int my_guard = 0, my_bad = 0;
     for (int k = threadIdx.x; k < nq; k += blockDim.x) {
         const int l = queue[k];
+        RVMC_DEV_ASSERT(l >= 0 && l < nslots);
         const uint64_t slot = slot0 + (uint64_t)l;
         const u32x4 wa = draw(slot, RVMC_STREAM_ORBIT_A);
         const u32x4 wb = draw(slot, RVMC_STREAM_ORBIT_B);
@@ -337,6 +343,7 @@ __global__ void __launch_bounds__(STATS_THREADS) point_stats_kernel(StatsArgs a)
                 if ((double)k * a.bin > xd) --k;
                 else if ((double)(k + 1) * a.bin <= xd) ++k;
                 if (k >= nb_mode && xd <= last_edge) k = nb_mode - 1;
+                RVMC_DEV_ASSERT(k >= -1 && k <= nb_mode);
                 if (k >= 0 && k < nb_mode) atomicAdd(&mode_hist[k], 1u);
             }
         };
@@ -371,6 +378,7 @@ __global__ void __launch_bounds__(STATS_THREADS) point_stats_kernel(StatsArgs a)
                 if (r < c) break;
                 r -= c;
             }
+            RVMC_DEV_ASSERT(d <= 255 && r < h[d]);          // the target rank lies inside the located digit
             rank[t] = r;
             prefix[t] = (prefix[t] << 8) | d;
         }
