@@ -32,6 +32,7 @@ struct BcArgs {
     uint64_t seed;                // (kept for the fp64 mass draw)
     int32_t nstars, max_epochs;
     int32_t star0;                // first star of this launch (gridDim.y is limited to 65535)
+    int32_t spt;                  // samples per thread
     int32_t first_star;           // global index of local star 0 (RNG counter only)
     const int32_t* n_epochs;      // [nstars]
     const double* t_obs;          // [nstars][max_epochs]  s
@@ -83,15 +84,15 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
 // NE    : compile-time bound on the epochs per star (<= 16: epoch loop fully unrolled, RVs in registers)
 // FAST  : the headline configuration with every launch-uniform switch resolved at compile time --
 //         measurement errors given, per-epoch RVs not written, one Halley step, fp64 guard proven
-//         unreachable by the host (guard_reachable()), phase convention QUIRK.  !FAST keeps all of
-//         them as run-time values (same arithmetic, ~15 % more instructions).
-// Each thread walks BC_SPT samples of its star, so the per-block prologue (epoch tables, pair
-// thresholds, two barriers) is amortised over BC_THREADS * BC_SPT binaries.
-#ifndef BC_SPT
-#define BC_SPT 2
-#endif
+//         unreachable by the host (guard_reachable()), period-law exponent 1 or 2, phase convention
+//         QUIRK.  !FAST keeps all of them as run-time values (same arithmetic, ~15 % more
+//         instructions, and a call to pow() for a general period-law exponent).
+// Each thread walks a.spt samples of its star (1..8, chosen by the host so that the grid still
+// holds >= 8 blocks per SM), so the per-block prologue (epoch tables, pair thresholds, two barriers)
+// is amortised over BC_THREADS * spt binaries.  3 blocks/SM at <= 85 registers measured best.
+#define BC_MAX_SPT 8
 #ifndef BC_MIN_BLOCKS
-#define BC_MIN_BLOCKS 1
+#define BC_MIN_BLOCKS 3
 #endif
 template <int NE, bool FAST, bool QUIRK>
 __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kernel(BcArgs a) {
@@ -136,9 +137,9 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
     __syncthreads();
 
     unsigned int my_guard = 0, my_bad = 0, my_det = 0;
-    const int64_t i_first = (int64_t)blockIdx.x * (BC_THREADS * BC_SPT) + threadIdx.x;
+    const int64_t i_first = (int64_t)blockIdx.x * (BC_THREADS * a.spt) + threadIdx.x;
 #pragma unroll 1
-    for (int rep = 0; rep < BC_SPT; ++rep) {
+    for (int rep = 0; rep < a.spt; ++rep) {
         const int64_t i = i_first + (int64_t)rep * BC_THREADS;
         if (i >= a.n_samples) break;
         const uint64_t sample = a.first_sample + (uint64_t)i;
@@ -153,13 +154,29 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
             o.log2m = (a.P32.mass.kind == POW_ONE) ? fast_lg2(a.P32.mass.minv * p)
                                                    : fmaf(a.P32.mass.inv, fast_lg2(p), a.P32.log2_mass_min);
         } else {
-            const double m = bc_mass_f64(a.P64, a.mass_mode, a.masses, a.mass_errors, star, a.seed, item, 0.0);
+            // masses at face value (:190) or N(masses, mass_errors) (:183); the normal is the fp32
+            // Box-Muller of the SAME words rvmc_biascorr_sample uses (1e-7 relative apart): the hot
+            // kernel stays free of fp64 transcendentals and of the function calls they bring
+            double m = a.masses[star];
+            if (a.mass_mode == 1) {
+                const u32x4 w = philox_block(a.key, item >> 1, RVMC_STREAM_MASS, 0);
+                float z0, z1;
+                box_muller_f32(w.x, w.y, z0, z1);
+                m = fma(a.mass_errors[star], (double)((item & 1) ? z1 : z0), m);
+            }
             o.log2m = fast_lg2((float)(m * (1.0 / RVMC_MSUN_KG)));     // m <= 0 -> NaN like the reference (Q12)
         }
         // Period in fp64: the phase needs ~1e-10 relative on P (2 pi t / P reaches ~2e3 turns).  Only
         // 1/P is ever needed: time = u P (RVMC_bias_corr.py:328), so t / P = t_obs / P + u, and the
         // eccentricity regimes compare log10 P.
-        const double xd = powerlaw_f64(a.P64.logp, u01_f64(wa.y));
+        double xd;
+        if constexpr (FAST) {
+            // exponent 1 or 2 only (pi = 0 or the Sana et al. -0.5): no pow(), no call, no stack frame
+            const double p = __dadd_rn(a.P64.logp.a, __dmul_rn(a.P64.logp.b, u01_f64(wa.y)));
+            xd = ((a.P64.logp.kind == POW_ONE) ? p : p * p) * a.P64.logp.minv;
+        } else {
+            xd = powerlaw_f64(a.P64.logp, u01_f64(wa.y));
+        }
         const double invP = exp10_fast_f64(-4.9365137424788932 - xd);   // 1 / (86400 * 10^x)  [1/s]
         o.x = (float)xd;
         const double uphase = u01_f64(wa.z);
@@ -261,8 +278,8 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
         if (my_bad) atomicAdd(&c_bad, my_bad);
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int64_t first = (int64_t)blockIdx.x * (BC_THREADS * BC_SPT);
-            const int64_t nvalid = min((int64_t)(BC_THREADS * BC_SPT), a.n_samples - first);
+            const int64_t first = (int64_t)blockIdx.x * (BC_THREADS * a.spt);
+            const int64_t nvalid = min((int64_t)(BC_THREADS * a.spt), a.n_samples - first);
             if (a.counters) {
                 atomicAdd(a.counters + 0, (unsigned long long)(nvalid * ne));
                 if (c_det) atomicAdd(a.counters + 1, (unsigned long long)c_det);
@@ -290,7 +307,8 @@ static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
 template <int NE>
 static int bc_dispatch(BcArgs& a, bool guard, int64_t blocks_per_star, cudaStream_t stream) {
     if constexpr (NE <= 8) {
-        const bool fast = a.rv_err != nullptr && a.rv_out == nullptr && a.kepler_iters == 1 && !guard;
+        const bool fast = a.rv_err != nullptr && a.rv_out == nullptr && a.kepler_iters == 1 && !guard &&
+                          a.P64.logp.kind != POW_GENERAL;
         if (fast)
             return a.quirk_phase ? bc_launch<NE, true, true>(a, blocks_per_star, stream)
                                  : bc_launch<NE, true, false>(a, blocks_per_star, stream);
@@ -517,7 +535,11 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
     a.rv_out = rv_out;
     a.counters = (unsigned long long*)counters;
     a.det_per_star = det_per_star;
-    const int64_t blocks_per_star = (n_samples + BC_THREADS * BC_SPT - 1) / (BC_THREADS * BC_SPT);
+    // samples per thread: as many as keep >= 8 blocks per SM in flight
+    int64_t spt = ((int64_t)nstars * n_samples) / ((int64_t)BC_THREADS * sm_count() * 8);
+    spt = spt < 1 ? 1 : (spt > BC_MAX_SPT ? BC_MAX_SPT : spt);
+    a.spt = (int32_t)spt;
+    const int64_t blocks_per_star = (n_samples + BC_THREADS * spt - 1) / (BC_THREADS * spt);
     if (blocks_per_star > 0x7fffffffLL) {
         set_error("too many samples in one launch (%lld); shard them", (long long)n_samples);
         return RVMC_ERR_UNSUPPORTED;
