@@ -298,11 +298,11 @@ def run_gpu_arm(args):
         # the binding ceiling is the issue rate (1 warp-instruction / clk / SM sub-partition), below the
         # SFU (17 ops) and FP32 (100 flop) ceilings.  peak = SMs x 4 x 32 x SM clock sampled under load.
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at the default size (ncu --set full,
-        # profiles/r01_biascorr_fused_fullsize_ncu.md): 126.7 KB + 442.26 MB; the algorithmic 500 MB of
+        # profiles/r01_biascorr_fused_fullsize_ncu.md): 150 KB + 442.22 MB; the algorithmic 500 MB of
         # results minus what still sits in the 126 MB L2 when the kernel ends
         traffic, traffic_src = args.traffic_bytes, "--traffic-bytes"
         if traffic is None and (nstars, ns) == (100, 10 ** 6):
-            traffic, traffic_src = 442.39e6, "profiles/r01_biascorr_fused_fullsize_ncu.md"
+            traffic, traffic_src = 442.37e6, "profiles/r01_biascorr_fused_fullsize_ncu.md"
         sms = C.c_int()
         _abi.check(lib.rvmc_device_info(local, C.byref(sms), None, None, None))
         clk_hz = 1e6 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
@@ -313,11 +313,12 @@ def run_gpu_arm(args):
                 "unit": "T lane-instr/s", "frac": rv_per_s_kernel * alg_instr / issue_peak,
                 "peak_source": "%d SMs x 4 schedulers x 32 lanes x %.0f MHz (NVML, sampled during the timed region)"
                                % (sms.value, clk_hz / 1e6),
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "rvmc::biascorr_fused_kernel<6,1,true>", "launch_ms": launch_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "rvmc::biascorr_fused_kernel<6, FAST, QUIRK>", "launch_ms": launch_ms,
                 "algorithmic_per_unit": {"fp32_flop": ALG_FP32_FLOP, "sfu_ops": ALG_SFU_OPS, "int_ops": ALG_INT_OPS,
                                          "fp64_flop": ALG_FP64_FLOP, "lane_instr": alg_instr, "hbm_bytes": ALG_HBM_BYTES},
-                "ncu": "profiles/r01_biascorr_fused_ncu.md: 80 % of issue slots busy, FMA 37 %, ALU 37 %, XU 41 %, "
-                       "FP64 9 %, tensor 0 %, DRAM 0.5 %",
+                "ncu": "profiles/r01_biascorr_fused_fullsize_ncu.md (same launch, ncu --set full): 79 % of issue slots "
+                       "busy, 188 executed thread-instructions per unit (178 algorithmic), FMA pipe 43 %, ALU 42 %, "
+                       "XU 52 %, FP64 5 %, tensor 0 %, DRAM throughput < 2 %",
                 "hbm": {"achieved": rv_per_s_kernel * ALG_HBM_BYTES / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "peak_source": "MEASURED_PEAKS.json" if peak_src == "measured" else "fallback 6650 GB/s",
                         "frac": rv_per_s_kernel * ALG_HBM_BYTES / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
