@@ -150,17 +150,28 @@ def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**
     if err.ndim != 1 or err.size != int(sample_size):
         raise ValueError("measured_errors must have sample_size = %d entries (got shape %s)"
                          % (int(sample_size), err.shape))
-    all_pts = _as_points(pops, seeds)
-    for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
-        if np.any(all_pts[f] == -1.0):
-            raise ZeroDivisionError("float division by zero")          # RVMC.py:112
     rank, world = dist_info(group) if distributed else (0, 1)
     local = shard_indices(n_points, rank, world)
+    nl = len(local)
+    if isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE:
+        # every rank checks ALL points (so that all ranks raise together) but copies only its share
+        for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
+            if np.any(pops[f] == -1.0):
+                raise ZeroDivisionError("float division by zero")          # RVMC.py:112
+        pts_np = np.ascontiguousarray(pops[rank::world])
+        if seeds is not None:
+            pts_np["seed"] = np.asarray(seeds, dtype=np.uint64)[rank::world]
+    else:
+        all_pts = _as_points(pops, seeds)
+        for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
+            if np.any(all_pts[f] == -1.0):
+                raise ZeroDivisionError("float division by zero")
+        pts_np = np.ascontiguousarray(all_pts[rank::world])
+    if not nl:
+        pts_np = np.zeros(1, dtype=POINT_DTYPE)
     dev = dv.resolve_device(device)
     t = dv.torch()
     ns = int(number_of_samples)
-    nl = len(local)
-    pts_np = np.ascontiguousarray(all_pts[rank::world]) if nl else np.zeros(1, dtype=POINT_DTYPE)
     pts = pts_np.ctypes.data_as(C.POINTER(_abi.GridPoint))
     stats_d = dv.zeros((max(nl, 1) * STATS_DTYPE.itemsize,), "uint8", dev)
     errd = dv.to_device(err, "float32", dev)
