@@ -1,4 +1,4 @@
-// librvmc_b200.so -- library plumbing (errors, device gate, workspace) and the two elementary
+// librvmc_b200.so -- library plumbing (errors, device gate) and the two elementary
 // generator entries (K1): raw Philox blocks and fp64 normals.
 //
 // Reference code replaced: np.random.normal at RVMC.py:101 (cluster_velocities) and RVMC.py:224
@@ -34,8 +34,6 @@ int cuda_status(cudaError_t e, const char* what) {
 struct DeviceState {
     int checked = 0;      // 0 = not yet, 1 = ok, -1 = unusable
     int sms = 0;
-    void* ws = nullptr;
-    size_t ws_bytes = 0;
 };
 static std::mutex g_mu;
 static std::vector<DeviceState> g_dev;
@@ -83,27 +81,6 @@ int sm_count() {
     int rc;
     DeviceState* s = current_state(&rc);
     return s ? s->sms : 0;
-}
-
-int workspace(size_t bytes, void** ptr) {
-    int rc;
-    DeviceState* s = current_state(&rc);
-    if (!s) return rc;
-    if (s->ws_bytes < bytes) {
-        // grow-only; the old block is released after the device drains so that kernels already
-        // queued on it stay valid
-        if (s->ws) {
-            RVMC_CUDA(cudaDeviceSynchronize());
-            RVMC_CUDA(cudaFree(s->ws));
-            s->ws = nullptr;
-            s->ws_bytes = 0;
-        }
-        size_t want = bytes + (bytes >> 2) + 4096;
-        RVMC_CUDA(cudaMalloc(&s->ws, want));
-        s->ws_bytes = want;
-    }
-    *ptr = s->ws;
-    return RVMC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -17,8 +17,6 @@ int cuda_status(cudaError_t e, const char* what);
 int require_device();
 // number of SMs of the current device (cached)
 int sm_count();
-// grow-only per-device workspace owned by the library (grid descriptors, tables)
-int workspace(size_t bytes, void** ptr);
 
 inline unsigned int blocks_for(int64_t n, int threads) {
     return (unsigned int)((n + threads - 1) / threads);
