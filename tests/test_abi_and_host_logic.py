@@ -184,3 +184,33 @@ def test_pmin_vs_age_join_and_fit(tmp_path):
     assert beta[0] == 1e5 and abs(beta[1] - 0.4) < 1e-3 and abs(beta[2] - 2.0) < 1e-2
     assert grid.quad_func([2.0, 1.0, 3.0], 0.0) == 5.0
     assert grid.read_best_fit_table(str(tmp_path / "Pmin_ObsSig_10.123_Nstars_12_Mass_6_20.dat"))["best_Pmin"] > 0
+
+
+def test_hot_kernels_resource_usage_and_instruction_mix(lib):
+    """Regression guard from the round-1 tuning: the FAST multi-epoch kernel and the single-population
+    fused sigma kernel must stay call-free (no stack frame: a callee such as pow() silently raised the
+    launch to 128 registers once) and within their occupancy budget; the library must contain no
+    tensor-core instruction (the path has no dense contraction) and must be sm_100a code."""
+    out = subprocess.run(["cuobjdump", "-res-usage", _abi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+    assert "sm_100a" in out
+    fast_bc = [k for k in usage if "biascorr_fused_kernelILi6ELb1" in k or "biascorr_fused_kernelILi8ELb1" in k]
+    assert len(fast_bc) == 4
+    for k in fast_bc:
+        assert usage[k][0] <= 85 and usage[k][1] == 0, (k, usage[k])            # 3 blocks of 256 threads per SM
+    single = [k for k in usage if "sigma1d_fused_kernelILb1ELi1ELb0" in k]
+    assert len(single) == 1 and usage[single[0]][0] <= 64 and usage[single[0]][1] == 0, usage[single[0]]
+    multi = [k for k in usage if "sigma1d_fused_kernelILb0ELi1ELb0" in k]
+    assert len(multi) == 1 and usage[multi[0]][0] <= 64
+    sass = subprocess.run(["cuobjdump", "-sass", _abi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "IMAD.WIDE.U32" in sass and "MUFU.EX2" in sass and "MUFU.LG2" in sass and "DFMA" in sass
+    for tensor_op in ("HMMA", "UTCHMMA", "UTCQMMA", "IMMA", "DMMA"):
+        assert tensor_op not in sass, tensor_op
