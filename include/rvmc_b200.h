@@ -276,6 +276,19 @@ RVMC_API int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, cons
                   rvmc_point_stats* stats_out, float* sigma_out, uint32_t* hist_out, float* scratch,
                   uint64_t* counters, void* cuda_stream);
 
+/* The binary-fraction axis of a grid in one pass.  Point i is evaluated for every fbins[k],
+ * k < n_fbins <= 32, with the point's own seed shared along the axis (pop.fbin is ignored): each star
+ * slot is sampled and solved once and the cluster is reduced once per fraction.  Results are
+ * BIT-IDENTICAL to rvmc_grid_run on n_points*n_fbins points {pop_i with fbin = fbins[k], seed_i} --
+ * this is an execution strategy, not a different estimator -- at roughly the cost of the largest
+ * fraction alone.  Layouts: stats_out [n_points][n_fbins], sigma_out [n_points][n_fbins][n_real],
+ * hist_out [n_points][n_fbins][hist_bins]; fbins is a HOST array; scratch as for rvmc_grid_run.
+ * sample_size <= 2048. */
+RVMC_API int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const double* fbins, int n_fbins,
+                        const float* meas_err, int sample_size, int weighted, int ddof, int64_t n_real,
+                        double bin, int hist_bins, rvmc_point_stats* stats_out, float* sigma_out,
+                        uint32_t* hist_out, float* scratch, uint64_t* counters, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

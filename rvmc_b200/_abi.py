@@ -103,6 +103,8 @@ SIGNATURES = {
     "rvmc_biascorr_singles": (_I, [_U64, _I, _I, _VP, _VP, _U64, _I64, _VP, _VP]),
     "rvmc_biascorr_detect": (_I, [_I, _I64, _I, _VP, _VP, _VP, _D, _D, _VP, _VP]),
     "rvmc_grid_scratch_slots": (_I, [_I]),
+    "rvmc_grid_run_fbins": (_I, [C.POINTER(GridPoint), _I64, C.POINTER(C.c_double), _I, _VP, _I, _I, _I, _I64, _D, _I,
+                                 _VP, _VP, _VP, _VP, _VP, _VP]),
     "rvmc_grid_run": (_I, [C.POINTER(GridPoint), _I64, _VP, _I, _I, _I, _I64, _D, _I, _VP, _VP, _VP, _VP,
                            _VP, _VP]),
 }

@@ -33,33 +33,34 @@ __device__ __forceinline__ T group_sum(T x, int G) {
     return x;
 }
 
-// v: [nr][S] in shared memory; wts: [S] weights 1/err^2 in shared memory or nullptr (unweighted);
-// wsum: sum of the weights; out[r] receives sigma of realization r.  All threads of the block
-// must call this (it contains warp shuffles); blockDim.x must be a multiple of 32.
-template <typename T, typename OutT>
-__device__ __forceinline__ void reduce_tile_sigma(const T* v, int nr, int S, int G, const T* wts, T wsum,
-                                                  int ddof, OutT* out) {
+// value(l): velocity of tile slot l = r*S + j (a functor over shared memory); wts: [S] weights
+// 1/err^2 in shared memory or nullptr (unweighted); wsum: sum of the weights; out[r] receives sigma
+// of realization r.  All threads of the block must call this (it contains warp shuffles);
+// blockDim.x must be a multiple of 32.
+template <typename T, typename OutT, typename Value>
+__device__ __forceinline__ void reduce_tile_sigma_fn(Value value, int nr, int S, int G, const T* wts, T wsum,
+                                                     int ddof, OutT* out) {
     const int ng = blockDim.x / G;          // groups per block
     const int gi = threadIdx.x / G;
     const int gl = threadIdx.x & (G - 1);
     const int iters = (nr + ng - 1) / ng;
+    RVMC_DEV_ASSERT(G >= 1 && G <= 32 && (G & (G - 1)) == 0 && gl < G);
     for (int it = 0; it < iters; ++it) {
         const int r = it * ng + gi;
         const bool valid = r < nr;
-        const T* row = v + (size_t)(valid ? r : 0) * S;
-        RVMC_DEV_ASSERT(G >= 1 && G <= 32 && (G & (G - 1)) == 0 && gl < G);
-        const T pivot = row[0];
+        const int base = (valid ? r : 0) * S;
+        const T pivot = value(base);
         T s1 = 0, s2 = 0;
         if (wts) {
             for (int j = gl; j < S; j += G) {
-                const T d = row[j] - pivot;
+                const T d = value(base + j) - pivot;
                 const T wd = wts[j] * d;
                 s1 += wd;
                 s2 = fma(wd, d, s2);
             }
         } else {
             for (int j = gl; j < S; j += G) {
-                const T d = row[j] - pivot;
+                const T d = value(base + j) - pivot;
                 s1 += d;
                 s2 = fma(d, d, s2);
             }
@@ -85,6 +86,13 @@ __device__ __forceinline__ void reduce_tile_sigma(const T* v, int nr, int S, int
             out[r] = (OutT)sqrt(var);
         }
     }
+}
+
+// v: [nr][S] in shared memory, row-major.
+template <typename T, typename OutT>
+__device__ __forceinline__ void reduce_tile_sigma(const T* v, int nr, int S, int G, const T* wts, T wsum,
+                                                  int ddof, OutT* out) {
+    reduce_tile_sigma_fn<T, OutT>([v](int l) { return v[l]; }, nr, S, G, wts, wsum, ddof, out);
 }
 
 }  // namespace rvmc

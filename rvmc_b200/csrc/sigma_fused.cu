@@ -190,6 +190,149 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Binary-fraction axis of a grid in ONE pass
+// ---------------------------------------------------------------------------------------------
+// Grid points that differ only in f_bin and share a seed consume identical draws: the same star
+// slots, the same orbits, the same noise -- only the coin threshold differs.  This kernel evaluates
+// every slot once (orbit solved iff its coin is below the LARGEST threshold) and then reduces the
+// tile once per binary fraction, selecting per slot  coin < thresh_k ? noise + rv : noise.  The
+// result for fraction k is BIT-IDENTICAL to sigma1d_fused_kernel run with fbin = fbins[k] and the
+// same seed (same integer coin compare, same fp32 adds, same reduction order), so this is purely an
+// execution strategy: an n_f-point axis costs about as much as its f_bin = max point alone.
+#define FBINS_MAX 32
+struct FbinArgs {
+    FusedArgs base;                 // points: one descriptor per (other-axes) point; coin_thresh unused
+    int32_t n_fbins;
+    uint32_t thresh[FBINS_MAX];     // ascending or not: thresh_max is computed on the host
+    uint32_t thresh_max;
+};
+
+template <int ITERS, bool GUARD>
+__global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FusedArgs& a = fa.base;
+    const int S = a.S;
+    const int T = a.R * S;
+    float* noise = reinterpret_cast<float*>(smem_raw);           // [T]
+    float* rv = noise + T;                                       // [T]
+    uint32_t* coin = reinterpret_cast<uint32_t*>(rv + T);        // [T] 24-bit coin of every slot
+    float* scale = reinterpret_cast<float*>(coin + T);           // [S]
+    float* wts = scale + S;                                      // [S]
+    uint16_t* queue = reinterpret_cast<uint16_t*>(wts + S);      // [T]
+    __shared__ FusedPoint pt;
+    __shared__ int qn;
+    __shared__ float wsum_s;
+    __shared__ unsigned int cnt_guard, cnt_bad;
+
+    const int64_t tile = blockIdx.x;
+    const int64_t point = tile / a.tiles_per_point;
+    const int64_t r0 = (tile - point * a.tiles_per_point) * a.R;
+    const int nr = (int)min((int64_t)a.R, a.n_real - r0);
+    const int nslots = nr * S;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.points + point);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&pt);
+        for (int i = threadIdx.x; i < (int)(sizeof(FusedPoint) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    if (threadIdx.x == 0) {
+        qn = 0;
+        cnt_guard = 0;
+        cnt_bad = 0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        const float e = a.meas_err[j];
+        scale[j] = slot_scale(pt.pop.sigma_dyn, e);
+        wts[j] = 1.0f / (e * e);
+    }
+    __syncthreads();
+    if (a.weighted && threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int j = 0; j < S; ++j) s += wts[j];
+        wsum_s = s;
+    }
+    const uint64_t seed = seed_of(pt);
+    const uint64_t slot0 = (a.first_real + (uint64_t)r0) * (uint64_t)S;
+    const uint64_t p_begin = slot0 >> 1;
+    const int npairs = (int)(((slot0 + nslots + 1) >> 1) - p_begin);
+    const float invS = 1.0f / (float)S;
+    const uint32_t thresh = fa.thresh_max;
+    const int lane = threadIdx.x & 31;
+
+    // ---- phase A: coins + noise (as sigma1d_fused_kernel, the coin itself is kept) ---------------
+    const int npairs_pad = (npairs + 31) & ~31;
+    for (int pi = threadIdx.x; pi < npairs_pad; pi += blockDim.x) {
+        bool bin0 = false, bin1 = false;
+        int l0 = 0, l1 = 0;
+        if (pi < npairs) {
+            const uint64_t pair = p_begin + pi;
+            const u32x4 w = philox_block(seed, pair, RVMC_STREAM_SLOT, 0);
+            float z0, z1;
+            box_muller_f32(w.z, w.w, z0, z1);
+            l0 = (int)(int64_t)(2 * pair - slot0);
+            l1 = l0 + 1;
+            RVMC_DEV_ASSERT(l0 >= -1 && l0 < nslots && l1 <= nslots);
+            if (l0 >= 0) {
+                const int r = (int)(((float)l0 + 0.5f) * invS);
+                noise[l0] = z0 * scale[l0 - r * S];
+                coin[l0] = w.x >> 8;
+                bin0 = (w.x >> 8) < thresh;
+            }
+            if (l1 < nslots) {
+                const int r = (int)(((float)l1 + 0.5f) * invS);
+                noise[l1] = z1 * scale[l1 - r * S];
+                coin[l1] = w.y >> 8;
+                bin1 = (w.y >> 8) < thresh;
+            }
+        }
+        const unsigned m0 = __ballot_sync(0xffffffffu, bin0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, bin1);
+        const int c0 = __popc(m0), c1 = __popc(m1);
+        int base = 0;
+        if (lane == 0 && (c0 + c1)) base = atomicAdd(&qn, c0 + c1);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned below = (1u << lane) - 1u;
+        RVMC_DEV_ASSERT(base >= 0 && base + c0 + c1 <= nslots);
+        if (bin0) queue[base + __popc(m0 & below)] = (uint16_t)l0;
+        if (bin1) queue[base + c0 + __popc(m1 & below)] = (uint16_t)l1;
+    }
+    __syncthreads();
+
+    // ---- phase B: one orbit per slot that is a binary under the largest fraction -------------------
+    const int nq = qn;
+    unsigned int my_guard = 0, my_bad = 0;
+    for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+        const int l = queue[k];
+        RVMC_DEV_ASSERT(l >= 0 && l < nslots);
+        const uint64_t slot = slot0 + (uint64_t)l;
+        const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, 0);
+        const u32x4 wb = philox_block(seed, slot, RVMC_STREAM_ORBIT_B, 0);
+        const OrbitF32 o = sample_orbit_f32(pt.pop, wa, wb);
+        int g, b;
+        rv[l] = orbit_rv_f32<ITERS, GUARD>(pt.pop, o, pt.kepler_iters, nullptr, g, b);
+        my_guard += g;
+        my_bad += b;
+    }
+    if (my_guard) atomicAdd(&cnt_guard, my_guard);
+    if (my_bad) atomicAdd(&cnt_bad, my_bad);
+    __syncthreads();
+
+    // ---- phase C: one reduction per binary fraction -------------------------------------------------
+    for (int k = 0; k < fa.n_fbins; ++k) {
+        const uint32_t thr = fa.thresh[k];
+        reduce_tile_sigma_fn<float, float>(
+            [=](int l) { return coin[l] < thr ? noise[l] + rv[l] : noise[l]; }, nr, S, a.G,
+            a.weighted ? wts : nullptr, wsum_s, a.ddof, a.sigma_out + (point * fa.n_fbins + k) * a.sigma_stride + r0);
+    }
+    if (a.counters && threadIdx.x == 0) {
+        atomicAdd(a.counters + 0, (unsigned long long)nq);
+        if (cnt_guard) atomicAdd(a.counters + 1, (unsigned long long)cnt_guard);
+        if (cnt_bad) atomicAdd(a.counters + 2, (unsigned long long)cnt_bad);
+    }
+}
+
 // Per-slot dump of what the fused kernel computes (parity/debug entry): same device functions,
 // same draws; the orbit is evaluated for every slot, `is_binary` says whether K4 would use it.
 __global__ void fused_trace_kernel(FusedPoint pt, const float* __restrict__ meas_err, int S, uint64_t first_slot,
@@ -682,6 +825,145 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     for (int k = 0; k < 2; ++k)
         if (ev_stats[k]) cudaEventDestroy(ev_stats[k]);
     if (side) cudaStreamDestroy(side);       // deferred by the runtime until its work has drained
+    cudaFreeAsync(ws, stream);
+    return rc;
+}
+
+int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const double* fbins, int n_fbins,
+                        const float* meas_err, int sample_size, int weighted, int ddof, int64_t n_real, double bin,
+                        int hist_bins, rvmc_point_stats* stats_out, float* sigma_out, uint32_t* hist_out,
+                        float* scratch, uint64_t* counters, void* cuda_stream) {
+    RVMC_DEVICE_GATE();
+    RVMC_REQUIRE(n_points >= 0, "n_points must be >= 0");
+    RVMC_REQUIRE(n_fbins >= 1 && n_fbins <= FBINS_MAX, "n_fbins must be in [1, %d] (got %d)", FBINS_MAX, n_fbins);
+    RVMC_REQUIRE(fbins != nullptr, "fbins is NULL");
+    RVMC_REQUIRE(n_real >= 1 && n_real < ((int64_t)1 << 31), "number_of_samples per grid point must be in [1, 2^31)");
+    RVMC_REQUIRE(ddof == 0 || ddof == 1, "ddof must be 0 or 1");
+    RVMC_REQUIRE(bin > 0.0, "bin must be > 0");
+    RVMC_REQUIRE(hist_out == nullptr || hist_bins >= 1, "hist_bins must be >= 1 when hist_out is given");
+    if (sample_size < 1) {
+        set_error("sample_size must be >= 1 (got %d)", sample_size);
+        return RVMC_ERR_INVALID;
+    }
+    if (sample_size > 2048) {
+        set_error("sample_size %d exceeds the 2048 stars per cluster the f_bin-fused kernel is built for", sample_size);
+        return RVMC_ERR_UNSUPPORTED;
+    }
+    FbinArgs fa;
+    fa.n_fbins = n_fbins;
+    fa.thresh_max = 0;
+    for (int k = 0; k < n_fbins; ++k) {
+        RVMC_REQUIRE(fbins[k] >= 0.0 && fbins[k] <= 1.0, "fbin must be in [0,1] (got %g)", fbins[k]);
+        fa.thresh[k] = (uint32_t)llrint(fbins[k] * 16777216.0);
+        fa.thresh_max = fa.thresh[k] > fa.thresh_max ? fa.thresh[k] : fa.thresh_max;
+    }
+    if (n_points == 0) return RVMC_OK;
+    RVMC_REQUIRE(points && meas_err && stats_out, "points, meas_err and stats_out are required");
+    RVMC_REQUIRE(sigma_out || scratch, "either sigma_out or scratch must be given");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+    std::vector<FusedPoint> host(n_points);
+    bool iters1 = true, guard = false;
+    int rc = RVMC_OK;
+    for (int64_t i = 0; i < n_points; ++i) {
+        rc = make_fused_point(points[i].pop, points[i].seed, &host[i]);
+        if (rc) return rc;
+        iters1 = iters1 && host[i].kepler_iters == 1;
+        guard = guard || guard_reachable(points[i].pop);
+    }
+    void* ws = nullptr;
+    RVMC_CUDA(cudaMallocAsync(&ws, sizeof(FusedPoint) * (size_t)n_points, stream));
+    rc = cuda_status(cudaMemcpyAsync(ws, host.data(), sizeof(FusedPoint) * (size_t)n_points, cudaMemcpyHostToDevice,
+                                     stream), "cudaMemcpyAsync(points)");
+    if (rc) {
+        cudaFreeAsync(ws, stream);
+        return rc;
+    }
+    const FusedPoint* d_points = (const FusedPoint*)ws;
+
+    const int S = sample_size;
+    const int T = 2048;
+    const int R = T / S;
+    const size_t slots = (size_t)R * S;
+    const size_t smem = slots * (2 * sizeof(float) + sizeof(uint32_t) + sizeof(uint16_t)) + 2 * (size_t)S * sizeof(float) + 16;
+    const int64_t tiles_per_point = (n_real + R - 1) / R;
+    // rows of sigma per batch: half the scratch (two halves alternate, as in rvmc_grid_run)
+    int64_t batch = (rvmc_grid_scratch_slots(0) / 2) / n_fbins;
+    if (sigma_out) batch = 0x7fff0000LL / tiles_per_point;
+    if (batch < 1) batch = 1;
+    if (batch * tiles_per_point > 0x7fff0000LL) batch = 0x7fff0000LL / tiles_per_point;
+    if (!sigma_out && (int64_t)n_fbins > rvmc_grid_scratch_slots(0) / 2) {
+        cudaFreeAsync(ws, stream);
+        set_error("scratch too small for %d binary fractions", n_fbins);
+        return RVMC_ERR_UNSUPPORTED;
+    }
+    const bool fast = iters1 && !guard;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
+    rc = cuda_status(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
+    for (int k = 0; k < 2 && !rc; ++k)
+        rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
+    if (!rc && smem > 48 * 1024) {
+        rc = cuda_status(cudaFuncSetAttribute(sigma1d_fused_fbins_kernel<1, false>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        if (!rc) rc = cuda_status(cudaFuncSetAttribute(sigma1d_fused_fbins_kernel<0, true>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    }
+    int64_t nb = 0;
+    for (int64_t p0 = 0; p0 < n_points && !rc; p0 += batch, ++nb) {
+        const int64_t np = (n_points - p0 < batch) ? n_points - p0 : batch;
+        const int half = (int)(nb & 1);
+        const int64_t rows = np * n_fbins;
+        float* sig = sigma_out ? sigma_out + (size_t)p0 * n_fbins * n_real
+                               : scratch + (size_t)half * (rvmc_grid_scratch_slots(0) / 2) * n_real;
+        if (!sigma_out && nb >= 2) rc = cuda_status(cudaStreamWaitEvent(stream, ev_stats[half], 0), "cudaStreamWaitEvent");
+        if (rc) break;
+        fa.base.points = d_points + p0;
+        fa.base.meas_err = meas_err;
+        fa.base.sigma_out = sig;
+        fa.base.counters = (unsigned long long*)counters;
+        fa.base.first_real = 0;
+        fa.base.n_real = n_real;
+        fa.base.sigma_stride = n_real;
+        fa.base.S = S;
+        fa.base.R = R;
+        // the group size of rvmc_grid_run for this S (its tiles hold 4096 slots): same summation
+        // grouping => bit-identical sigmas
+        fa.base.G = reduce_group_size(S, S >= 4096 ? 1 : 4096 / S, 256);
+        fa.base.tiles_per_point = (int32_t)tiles_per_point;
+        fa.base.weighted = weighted;
+        fa.base.ddof = ddof;
+        const unsigned int total = (unsigned int)(tiles_per_point * np);
+        if (fast)
+            sigma1d_fused_fbins_kernel<1, false><<<total, 256, smem, stream>>>(fa);
+        else
+            sigma1d_fused_fbins_kernel<0, true><<<total, 256, smem, stream>>>(fa);
+        rc = cuda_status(cudaGetLastError(), "sigma1d_fused_fbins_kernel launch");
+        if (!rc) rc = cuda_status(cudaEventRecord(ev_fused, stream), "cudaEventRecord");
+        if (!rc) rc = cuda_status(cudaStreamWaitEvent(side, ev_fused, 0), "cudaStreamWaitEvent");
+        if (rc) break;
+        StatsArgs sa;
+        sa.sigma = sig;
+        sa.sigma_stride = n_real;
+        sa.n_real = n_real;
+        sa.bin = bin;
+        sa.hist_bins = hist_bins;
+        sa.stats_out = stats_out + p0 * n_fbins;
+        sa.hist_out = hist_out ? hist_out + (size_t)p0 * n_fbins * hist_bins : nullptr;
+        point_stats_kernel<<<(unsigned int)rows, STATS_THREADS, 0, side>>>(sa);
+        rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
+        if (!rc) rc = cuda_status(cudaEventRecord(ev_stats[half], side), "cudaEventRecord");
+    }
+    for (int k = 0; k < 2; ++k)
+        if (ev_stats[k] && nb > k) {
+            int rc2 = cuda_status(cudaStreamWaitEvent(stream, ev_stats[k], 0), "cudaStreamWaitEvent");
+            if (!rc) rc = rc2;
+        }
+    if (ev_fused) cudaEventDestroy(ev_fused);
+    for (int k = 0; k < 2; ++k)
+        if (ev_stats[k]) cudaEventDestroy(ev_stats[k]);
+    if (side) cudaStreamDestroy(side);
     cudaFreeAsync(ws, stream);
     return rc;
 }

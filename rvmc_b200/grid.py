@@ -199,6 +199,89 @@ def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**
     return out
 
 
+def run_points_fbins(pops, seeds, fbins, measured_errors, sample_size, number_of_samples=10**5, bin=0.5, ddof=0,
+                     weighted=False, keep_sigma=False, device=None, group=None, distributed=True):
+    """Like run_points for the Cartesian product (points x fbins) with each point's seed shared along
+    the f_bin axis: rvmc_grid_run_fbins samples and solves every star slot once and reduces once per
+    binary fraction -- bit-identical to run_points on the expanded list, at about the cost of the
+    largest fraction alone.  Returns 'stats' [n_points, n_fbins] (every rank), 'sigma'
+    [n_local, n_fbins, n_real] or None, 'counters', 'local'."""
+    if not (isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE):
+        pops = _as_points(pops, seeds)
+        seeds = None
+    n_points = len(pops)
+    fb = np.ascontiguousarray(fbins, dtype=np.float64).ravel()
+    if fb.size < 1:
+        raise ValueError("need at least one binary fraction")
+    err = np.ascontiguousarray(measured_errors, dtype=np.float32)
+    if err.ndim != 1 or err.size != int(sample_size):
+        raise ValueError("measured_errors must have sample_size = %d entries (got shape %s)"
+                         % (int(sample_size), err.shape))
+    for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
+        if np.any(pops[f] == -1.0):
+            raise ZeroDivisionError("float division by zero")          # RVMC.py:112
+    rank, world = dist_info(group) if distributed else (0, 1)
+    local = shard_indices(n_points, rank, world)
+    nl = len(local)
+    pts_np = np.ascontiguousarray(pops[rank::world])
+    if seeds is not None:
+        pts_np["seed"] = np.asarray(seeds, dtype=np.uint64)[rank::world]
+    if not nl:
+        pts_np = np.zeros(1, dtype=POINT_DTYPE)
+    dev = dv.resolve_device(device)
+    ns = int(number_of_samples)
+    item = STATS_DTYPE.itemsize
+    stats_all = np.empty((n_points, fb.size), dtype=STATS_DTYPE)
+    sigma_all = np.empty((nl, fb.size, ns), dtype=np.float32) if keep_sigma and nl else None
+    errd = dv.to_device(err, "float32", dev)
+    counters = dv.zeros((4,), "int64", dev)
+    pts = pts_np.ctypes.data_as(C.POINTER(_abi.GridPoint))
+    with dv.DeviceGuard(dev):
+        lib = _abi.lib()
+        for k0 in range(0, fb.size, 32):                      # the kernel takes <= 32 fractions per pass
+            sub = np.ascontiguousarray(fb[k0:k0 + 32])
+            nf = sub.size
+            stats_d = dv.zeros((max(nl, 1) * nf * item,), "uint8", dev)
+            sigma_d = dv.empty((nl, nf, ns), "float32", dev) if keep_sigma and nl else None
+            scratch = None
+            if sigma_d is None and nl:
+                scratch = dv.empty((lib.rvmc_grid_scratch_slots(dev.index), ns), "float32", dev)
+            _abi.check(lib.rvmc_grid_run_fbins(pts, nl, sub.ctypes.data_as(C.POINTER(C.c_double)), nf, dv.ptr(errd),
+                                               int(sample_size), int(bool(weighted)), int(ddof), ns, float(bin), 1,
+                                               dv.ptr(stats_d), dv.ptr(sigma_d), None, dv.ptr(scratch),
+                                               dv.ptr(counters), dv.stream_ptr(dev)))
+            # gather rows of nf records per point
+            flat = gather_point_stats_rows(stats_d[:nl * nf * item], n_points, nf, rank, world, group)
+            stats_all[:, k0:k0 + nf] = flat
+            if sigma_d is not None:
+                sigma_all[:, k0:k0 + nf] = dv.to_host(sigma_d)
+    bad = int(stats_all["reserved"].sum())
+    if bad:
+        raise NotImplementedError("%d grid points have sigma_1D histograms wider than the %d bins the statistics "
+                                  "kernel holds; use a larger `bin`" % (bad, 8192))
+    return dict(stats=stats_all, local=local, counters=dv.to_host(counters), sigma=sigma_all)
+
+
+def gather_point_stats_rows(local_bytes, n_points, row_len, rank, world, group=None):
+    """gather_point_stats for `row_len` consecutive records per point -> [n_points, row_len]."""
+    import torch
+    item = STATS_DTYPE.itemsize * row_len
+    if world == 1:
+        return np.frombuffer(local_bytes.detach().cpu().numpy().tobytes(), dtype=STATS_DTYPE).reshape(n_points, row_len).copy()
+    import torch.distributed as dist
+    n_max = (n_points + world - 1) // world
+    pad = torch.zeros(n_max * item, dtype=torch.uint8, device=local_bytes.device)
+    pad[:local_bytes.numel()] = local_bytes
+    out = torch.empty(world * n_max * item, dtype=torch.uint8, device=local_bytes.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    raw = np.frombuffer(out.cpu().numpy().tobytes(), dtype=STATS_DTYPE).reshape(world, n_max, row_len)
+    res = np.empty((n_points, row_len), dtype=STATS_DTYPE)
+    for r in range(world):
+        idx = shard_indices(n_points, r, world)
+        res[idx] = raw[r, :len(idx)]
+    return res
+
+
 def _pop_for(min_mass, max_mass, fbin, min_period, max_period, sigma_dyn, **extra):
     return _abi.PopParams.defaults(min_mass=float(min_mass), max_mass=float(max_mass), fbin=float(fbin),
                                    min_period=float(min_period), max_period=float(max_period),
@@ -435,25 +518,49 @@ def run_bigGrid(number_stars=20, min_mass=6, max_mass=20, n_fbin=100, n_pmin=100
 
 def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samples=10 ** 5, observed_sigma=None,
                 base=None, bin=0.5, ddof=0, seed=1, device=None, common_random_numbers=False, group=None,
-                usemode=False):
+                usemode=False, share_fbin_draws=True, distributed=True):
     """Generalised grid (BASELINE config 5): `axes` maps population parameter names (any field of
     rvmc_pop_params: 'period_pi', 'mass_ratio_kappa', 'fbin', 'min_period', ...) to 1-D value
     arrays; the Cartesian product is evaluated, sharded over the ranks of the current
     torch.distributed job.  Returns a dict with the per-point statistics reshaped to the grid, the
     aggregated counters, and -- when `observed_sigma` is given -- the best-fit multi-index
-    (argmin |median - observed|, first minimum in C order, the rule of :138-158)."""
+    (argmin |median - observed|, first minimum in C order, the rule of :138-158).
+
+    `share_fbin_draws=True` (default): grid points that differ only in `fbin` use the same seed, which
+    lets one kernel pass evaluate the whole f_bin axis (rvmc_grid_run_fbins; bit-identical to evaluating
+    those points one by one with that seed).  Each cell still gets `number_of_samples` realizations with
+    the exact per-cell distribution of the reference; only the noise of neighbouring f_bin cells is
+    correlated (which steadies the surface).  `False` gives every cell its own seed."""
     names = list(axes.keys())
     vals = [np.asarray(axes[k], dtype=np.float64) for k in names]
     shape = tuple(len(v) for v in vals)
-    mesh = np.meshgrid(*vals, indexing="ij")
-    flat = [m.ravel() for m in mesh]
-    cols = dict(base or {})
-    cols.update({k: f for k, f in zip(names, flat)})
-    pops = points_array(int(np.prod(shape)), **cols)
-    res = run_points(pops, point_seeds(seed, len(pops), common_random_numbers), _errs(measured_errors, sample_size),
-                     sample_size, number_of_samples, bin=bin, ddof=ddof, device=device, group=group)
-    out = dict(axes=dict(zip(names, vals)), shape=shape, stats=res["stats"].reshape(shape), counters=res["counters"],
-               n_local=len(res["local"]))
+    fused_axis = names.index("fbin") if (share_fbin_draws and "fbin" in names) else None
+    if fused_axis is None:
+        mesh = np.meshgrid(*vals, indexing="ij")
+        cols = dict(base or {})
+        cols.update({k: m.ravel() for k, m in zip(names, mesh)})
+        pops = points_array(int(np.prod(shape)), **cols)
+        res = run_points(pops, point_seeds(seed, len(pops), common_random_numbers),
+                         _errs(measured_errors, sample_size), sample_size, number_of_samples, bin=bin, ddof=ddof,
+                         device=device, group=group, distributed=distributed)
+        stats = res["stats"].reshape(shape)
+    else:
+        # the f_bin axis shares each point's draws and is evaluated in one pass (rvmc_grid_run_fbins)
+        o_names = [k for k in names if k != "fbin"]
+        o_vals = [v for k, v in zip(names, vals) if k != "fbin"]
+        o_shape = tuple(len(v) for v in o_vals)
+        n_other = int(np.prod(o_shape)) if o_shape else 1
+        cols = dict(base or {})
+        if o_vals:
+            mesh = np.meshgrid(*o_vals, indexing="ij")
+            cols.update({k: m.ravel() for k, m in zip(o_names, mesh)})
+        pops = points_array(n_other, **cols)
+        res = run_points_fbins(pops, point_seeds(seed, n_other, common_random_numbers), vals[fused_axis],
+                               _errs(measured_errors, sample_size), sample_size, number_of_samples, bin=bin,
+                               ddof=ddof, device=device, group=group, distributed=distributed)
+        stats = np.moveaxis(res["stats"].reshape(o_shape + (shape[fused_axis],)), -1, fused_axis)
+    out = dict(axes=dict(zip(names, vals)), shape=shape, stats=np.ascontiguousarray(stats), counters=res["counters"],
+               n_local=len(res["local"]), fbin_axis_fused=fused_axis is not None)
     if observed_sigma is not None:
         central = out["stats"]["mode" if usemode else "median"].ravel()
         d = np.abs(central - observed_sigma)

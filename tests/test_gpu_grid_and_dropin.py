@@ -67,6 +67,35 @@ def test_grid_scratch_path_equals_sigma_path_and_batches():
     assert st["median"] == 0 and st["p95"] == 0 and st["mean"] == 0 and st["n_hist_bins"] == 0 and np.isnan(st["mode"])
 
 
+@pytest.mark.parametrize("S,weighted,ddof,n_real", [(12, 0, 0, 5000), (5, 0, 1, 3001), (44, 1, 0, 700), (100, 0, 0, 300),
+                                                   (2048, 0, 1, 5)])
+def test_fbin_axis_in_one_pass_is_bit_identical_to_pointwise(S, weighted, ddof, n_real):
+    """rvmc_grid_run_fbins: every binary fraction of a point from ONE evaluation of its star slots,
+    bit-identical to rvmc_grid_run on the expanded point list with the seed shared along f_bin."""
+    pops = grid.points_array(5, period_pi=np.linspace(-0.9, 0.3, 5), mass_ratio_kappa=np.linspace(0.8, -0.8, 5),
+                             min_period=[1.4, 1.4, 30.0, 1.4, 3.0], sigma_dyn=[2.0, 0.0, 2.0, 5.0, 2.0])
+    seeds = grid.point_seeds(2027, 5)
+    fbins = np.array([0.7, 0.0, 1.0, 0.12, 0.999, 0.5])                       # unsorted on purpose
+    err = np.resize(M17, S)
+    a = grid.run_points_fbins(pops, seeds, fbins, err, S, n_real, ddof=ddof, weighted=bool(weighted), keep_sigma=True,
+                              distributed=False)
+    exp = np.repeat(pops, len(fbins))
+    exp["fbin"] = np.tile(fbins, 5)
+    b = grid.run_points(exp, np.repeat(seeds, len(fbins)), err, S, n_real, ddof=ddof, weighted=bool(weighted),
+                        keep_sigma=True, distributed=False)
+    np.testing.assert_array_equal(a["sigma"].reshape(-1, n_real), b["sigma"])
+    for k in grid.STATS_DTYPE.names:
+        if k not in ("n_guard", "n_nonconverged", "reserved"):
+            np.testing.assert_array_equal(a["stats"][k].ravel(), b["stats"][k], err_msg=k)
+    # far fewer orbits are solved: once per slot under the largest fraction (1.0 here)
+    assert a["counters"][0] == 5 * n_real * S and b["counters"][0] > 3 * a["counters"][0]
+    # more than 32 fractions go out in chunks of the same draws
+    many = np.linspace(0, 1, 40)
+    c = grid.run_points_fbins(pops[:2], seeds[:2], many, err, S, min(n_real, 500), ddof=ddof, weighted=bool(weighted),
+                              distributed=False)
+    assert c["stats"].shape == (2, 40) and np.all(np.diff(c["stats"]["mean"], axis=1) >= -0.35)
+
+
 def test_reference_entry_points_and_best_fit(tmp_path):
     t = grid.get_Pdistr_stats(measured_errors=M17, sample_size=12, pmin=1.4, pmax=3500, Npoints=12, bin=0.5, fbin=0.7,
                               min_mass=6, max_mass=20, number_of_samples=20000, seed=3)

@@ -40,11 +40,18 @@ def main():
     dist.all_reduce(cnt)
     ok = True
     if rank == 0:
-        single = grid.run_points(grid.points_array(int(np.prod(r["shape"])),
-                                                   **{k: m.ravel() for k, m in zip(axes, np.meshgrid(*axes.values(), indexing="ij"))}),
-                                 grid.point_seeds(11, int(np.prod(r["shape"]))), grid.M17_ERRORS, 12, n_real,
-                                 distributed=False)
-        same = all(np.array_equal(single["stats"][k], r["stats"][k].ravel()) for k in grid.STATS_DTYPE.names)
+        single = grid.grid_search(axes, number_of_samples=n_real, seed=11, observed_sigma=25.0, distributed=False)
+        same = all(np.array_equal(single["stats"][k], r["stats"][k]) for k in grid.STATS_DTYPE.names)
+        # and the f_bin-fused pass against plain point-by-point evaluation with the same seeds
+        plain = grid.grid_search(axes, number_of_samples=n_real, seed=11, share_fbin_draws=False, distributed=False)
+        n_other = len(axes["period_pi"]) * len(axes["mass_ratio_kappa"])
+        seeds = np.repeat(grid.point_seeds(11, n_other), len(axes["fbin"]))
+        mesh = np.meshgrid(*axes.values(), indexing="ij")
+        expanded = grid.run_points(grid.points_array(seeds.size, **{k: m.ravel() for k, m in zip(axes, mesh)}), seeds,
+                                   grid.M17_ERRORS, 12, n_real, distributed=False)
+        same = same and all(np.array_equal(expanded["stats"][k], r["stats"][k].ravel()) for k in
+                            ("median", "mean", "mode", "p05", "p95", "sigma_max"))
+        assert plain["stats"].shape == r["stats"].shape
         ok = ok and same and int(cnt[0]) == int(single["counters"][0])
         print(json.dumps({"check": "grid sharded == single GPU", "world": world, "points": int(np.prod(r["shape"])),
                           "identical": bool(same), "binary_rvs_all_ranks": int(cnt[0]),
