@@ -213,7 +213,13 @@ RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float*
     const float shape = kepler_shape_f32<ITERS, GUARD>(6.283185307179586f * aphase, RVMC_TWO_PI * (double)aphase,
                                          o.phase < 0.0f, o.e, rome2, sw, cw, iters, P.guard_amp, guard, bad);
     if (K_out) *K_out = K;
+    // a rounded product, never contracted into the caller's accumulation: every kernel that adds this
+    // RV to a noise term then produces the same bits (sigma1d_fused_kernel / sigma1d_fused_fbins_kernel)
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(K, shape);
+#else
     return K * shape;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
