@@ -200,12 +200,13 @@ def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**
 
 
 def run_points_fbins(pops, seeds, fbins, measured_errors, sample_size, number_of_samples=10**5, bin=0.5, ddof=0,
-                     weighted=False, keep_sigma=False, device=None, group=None, distributed=True):
+                     weighted=False, keep_sigma=False, keep_hist=False, hist_bins=2048, device=None, group=None,
+                     distributed=True):
     """Like run_points for the Cartesian product (points x fbins) with each point's seed shared along
     the f_bin axis: rvmc_grid_run_fbins samples and solves every star slot once and reduces once per
     binary fraction -- bit-identical to run_points on the expanded list, at about the cost of the
     largest fraction alone.  Returns 'stats' [n_points, n_fbins] (every rank), 'sigma'
-    [n_local, n_fbins, n_real] or None, 'counters', 'local'."""
+    [n_local, n_fbins, n_real] or None, 'hist' [n_local, n_fbins, hist_bins] or None, 'counters', 'local'."""
     if not (isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE):
         pops = _as_points(pops, seeds)
         seeds = None
@@ -233,6 +234,7 @@ def run_points_fbins(pops, seeds, fbins, measured_errors, sample_size, number_of
     item = STATS_DTYPE.itemsize
     stats_all = np.empty((n_points, fb.size), dtype=STATS_DTYPE)
     sigma_all = np.empty((nl, fb.size, ns), dtype=np.float32) if keep_sigma and nl else None
+    hist_all = np.zeros((nl, fb.size, int(hist_bins)), dtype=np.uint32) if keep_hist and nl else None
     errd = dv.to_device(err, "float32", dev)
     counters = dv.zeros((4,), "int64", dev)
     pts = pts_np.ctypes.data_as(C.POINTER(_abi.GridPoint))
@@ -243,23 +245,27 @@ def run_points_fbins(pops, seeds, fbins, measured_errors, sample_size, number_of
             nf = sub.size
             stats_d = dv.zeros((max(nl, 1) * nf * item,), "uint8", dev)
             sigma_d = dv.empty((nl, nf, ns), "float32", dev) if keep_sigma and nl else None
+            hist_d = dv.zeros((nl, nf, int(hist_bins)), "int32", dev) if keep_hist and nl else None
             scratch = None
             if sigma_d is None and nl:
                 scratch = dv.empty((lib.rvmc_grid_scratch_slots(dev.index), ns), "float32", dev)
             _abi.check(lib.rvmc_grid_run_fbins(pts, nl, sub.ctypes.data_as(C.POINTER(C.c_double)), nf, dv.ptr(errd),
-                                               int(sample_size), int(bool(weighted)), int(ddof), ns, float(bin), 1,
-                                               dv.ptr(stats_d), dv.ptr(sigma_d), None, dv.ptr(scratch),
+                                               int(sample_size), int(bool(weighted)), int(ddof), ns, float(bin),
+                                               int(hist_bins), dv.ptr(stats_d), dv.ptr(sigma_d), dv.ptr(hist_d),
+                                               dv.ptr(scratch),
                                                dv.ptr(counters), dv.stream_ptr(dev)))
             # gather rows of nf records per point
             flat = gather_point_stats_rows(stats_d[:nl * nf * item], n_points, nf, rank, world, group)
             stats_all[:, k0:k0 + nf] = flat
             if sigma_d is not None:
                 sigma_all[:, k0:k0 + nf] = dv.to_host(sigma_d)
+            if hist_d is not None:
+                hist_all[:, k0:k0 + nf] = dv.to_host(hist_d).view(np.uint32)
     bad = int(stats_all["reserved"].sum())
     if bad:
         raise NotImplementedError("%d grid points have sigma_1D histograms wider than the %d bins the statistics "
                                   "kernel holds; use a larger `bin`" % (bad, 8192))
-    return dict(stats=stats_all, local=local, counters=dv.to_host(counters), sigma=sigma_all)
+    return dict(stats=stats_all, local=local, counters=dv.to_host(counters), sigma=sigma_all, hist=hist_all)
 
 
 def gather_point_stats_rows(local_bytes, n_points, row_len, rank, world, group=None):
@@ -480,24 +486,37 @@ def find_Pmin_fbin_individual_clulsters(name_cluster, observed_dispersion, numbe
 
 
 def run_bigGrid(number_stars=20, min_mass=6, max_mass=20, n_fbin=100, n_pmin=100, number_of_samples=10 ** 5,
-                seed=None, device=None, outdir="results", write=True, common_random_numbers=False):
+                seed=None, device=None, outdir="results", write=True, common_random_numbers=False,
+                share_fbin_draws=True):
     """The (f_bin x P_min) grid of findBestDistributions.py:457-489 in ONE sharded launch sequence.
     Pickles (binary mode) the reference's list of per-f_bin dicts {values, bins, period, fbin, mean,
     median, mode, p05, p16, p84, p95} and returns it (rank 0 writes the file)."""
     fbins = np.linspace(0, 1, n_fbin)
     periods = np.logspace(np.log10(1.4), np.log10(3500), n_pmin)
     RV_errors = np.ones(number_stars) * 1.2
-    pops = [_pop_for(min_mass, max_mass, f, p, 3500, 2.0) for f in fbins for p in periods]
     sd = dv.fresh_seed() if seed is None else seed
-    res = run_points(pops, point_seeds(sd, len(pops), common_random_numbers), RV_errors, number_stars,
-                     number_of_samples, bin=0.5, ddof=0, keep_hist=(dist_info()[1] == 1), device=device)
-    st = res["stats"].reshape(n_fbin, n_pmin)
+    single = dist_info()[1] == 1
+    if share_fbin_draws:
+        # one seed per P_min column, shared by its 100 binary fractions: the whole f_bin axis of a
+        # column comes out of one pass over its star slots (rvmc_grid_run_fbins)
+        pops = points_array(n_pmin, min_mass=float(min_mass), max_mass=float(max_mass), min_period=periods,
+                            max_period=3500.0, sigma_dyn=2.0)
+        res = run_points_fbins(pops, point_seeds(sd, n_pmin, common_random_numbers), fbins, RV_errors, number_stars,
+                               number_of_samples, bin=0.5, ddof=0, keep_hist=single, device=device)
+        st = res["stats"].T                                              # [n_fbin, n_pmin]
+        hist = None if res["hist"] is None else np.transpose(res["hist"], (1, 0, 2))
+    else:
+        pops = [_pop_for(min_mass, max_mass, f, p, 3500, 2.0) for f in fbins for p in periods]
+        res = run_points(pops, point_seeds(sd, len(pops), common_random_numbers), RV_errors, number_stars,
+                         number_of_samples, bin=0.5, ddof=0, keep_hist=single, device=device)
+        st = res["stats"].reshape(n_fbin, n_pmin)
+        hist = None if res["hist"] is None else res["hist"].reshape(n_fbin, n_pmin, -1)
     l_res = []
     for a, fbin in enumerate(fbins):
         result = dict()
         row = st[a]
-        if res["hist"] is not None:
-            h = res["hist"].reshape(n_fbin, n_pmin, -1)[a]
+        if hist is not None:
+            h = hist[a]
             result['values'] = [h[b, :row["n_hist_bins"][b]] / max(1.0, 0.5 * h[b].sum()) for b in range(n_pmin)]
         else:
             result['values'] = None

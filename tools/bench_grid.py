@@ -38,24 +38,27 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
     grid.grid_search({k: v[:4] for k, v in axes.items()}, number_of_samples=1000, seed=1)      # warm-up
-    times = []
-    for rep in range(3):
-        barrier()
-        t0 = time.perf_counter()
-        r = grid.grid_search(axes, number_of_samples=n_real, seed=2024 + rep, observed_sigma=25.0)
-        barrier()
-        times.append(time.perf_counter() - t0)
-    cnt = torch.from_numpy(r["counters"].astype(np.int64)).to(dev)
-    if world > 1:
-        dist.all_reduce(cnt)
-    if rank == 0:
-        npts = int(np.prod(r["shape"]))
-        dt = min(times)
-        print(json.dumps({"case": "C5 grid %dx%dx%d x %d realizations x 12 stars" % (n[0], n[1], n[2], n_real),
-                          "n_gpus": world, "points": npts, "seconds_best_of_3": dt, "seconds_all": times,
-                          "points_per_s": npts / dt, "binary_rvs_per_s": float(cnt[0]) / dt, "scaling": "strong",
-                          "best_index": r["best_index"], "best_params": r["best_params"],
-                          "median_range": [float(r["stats"]["median"].min()), float(r["stats"]["median"].max())]}))
+    for share in (True, False):
+        times = []
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            r = grid.grid_search(axes, number_of_samples=n_real, seed=2024, observed_sigma=25.0, share_fbin_draws=share)
+            barrier()
+            times.append(time.perf_counter() - t0)
+        cnt = torch.from_numpy(r["counters"].astype(np.int64)).to(dev)
+        if world > 1:
+            dist.all_reduce(cnt)
+        if rank == 0:
+            npts = int(np.prod(r["shape"]))
+            dt = min(times)
+            print(json.dumps({"case": "C5 grid %dx%dx%d x %d realizations x 12 stars" % (n[0], n[1], n[2], n_real),
+                              "fbin_axis": "one pass, draws shared along f_bin (rvmc_grid_run_fbins)" if share else
+                              "independent draws per cell (rvmc_grid_run)",
+                              "n_gpus": world, "points": npts, "seconds_best_of_3": dt, "seconds_all": times,
+                              "points_per_s": npts / dt, "binary_rvs_solved_per_s": float(cnt[0]) / dt,
+                              "scaling": "strong", "best_index": r["best_index"], "best_params": r["best_params"],
+                              "median_range": [float(r["stats"]["median"].min()), float(r["stats"]["median"].max())]}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
