@@ -378,15 +378,25 @@ __global__ void fused_trace_kernel(FusedPoint pt, const float* __restrict__ meas
 // K6: per-point statistics of the sigma_1D distribution (findBestDistributions.py:47-60)
 // ---------------------------------------------------------------------------------------------
 // One block per point.  Exact order statistics by a most-significant-digit radix select on the
-// float bit patterns (sigma >= 0, so the unsigned order is the numeric order): four passes of 8
-// bits over the point's sigma array, which the fused kernel has just written and is L2 resident.
-// The ten ranks needed for the 5/16/50/84/95 percentiles (NumPy 'linear' rule: virtual index
-// q/100*(n-1), neighbours floor and floor+1) are selected together; targets that share a prefix
-// share a histogram.  The same passes accumulate the mean (fp64) and the maximum; the `bin`-wide
-// histogram for the mode (first maximal bin, :49-52) is filled in pass 2 once the maximum is known.
+// float bit patterns (sigma >= 0, so the unsigned order is the numeric order) in three passes of
+// 12 + 10 + 10 bits over the point's sigma array, which the fused kernel has just written and is L2
+// resident.  The ten ranks needed for the 5/16/50/84/95 percentiles (NumPy 'linear' rule: virtual
+// index q/100*(n-1), neighbours floor and floor+1) are selected together:
+//   pass 0  one 4096-bin histogram of the top 12 bits (run-length cached per thread: neighbouring
+//           values share them) + the sum (fp64) and the maximum;
+//   pass 1  elements whose top 12 bits carry a target (one byte-table lookup) go to that prefix
+//           group's 1024-bin histogram of the next 10 bits; the `bin`-wide histogram for the mode
+//           (first maximal bin, :49-52) is filled here, now that the maximum is known;
+//   pass 2  a second table keyed by (group, middle digit) routes the few remaining candidates to
+//           the histogram of the last 10 bits.
+// ~45 instructions per element in total; targets that share a prefix share a histogram.
 #define STATS_THREADS 512
 #define STATS_TARGETS 10
-#define STATS_MODE_BINS_MAX 8192
+#define STATS_MODE_BINS_MAX 4096
+#define STATS_B0 12
+#define STATS_B1 10
+#define STATS_B2 10
+#define STATS_SMEM_BYTES (((STATS_TARGETS << STATS_B1) + STATS_MODE_BINS_MAX) * 4 + (1 << STATS_B0) + (STATS_TARGETS << STATS_B1))
 
 struct StatsArgs {
     const float* sigma;        // [n_points][sigma_stride]
@@ -415,69 +425,119 @@ __device__ __forceinline__ double block_sum_f64(double x, double* scratch) {
     return tot;
 }
 
-__global__ void __launch_bounds__(STATS_THREADS) point_stats_kernel(StatsArgs a) {
-    __shared__ unsigned int hist[STATS_TARGETS][256];
-    __shared__ unsigned int mode_hist[STATS_MODE_BINS_MAX];
+// thread t < STATS_TARGETS: locate the digit holding rank r inside histogram h[0..nbins)
+__device__ __forceinline__ unsigned int locate_digit(const unsigned int* h, int nbins, unsigned int& r) {
+    unsigned int d = 0;
+    for (; d < (unsigned int)nbins - 1; ++d) {
+        const unsigned int c = h[d];
+        if (r < c) break;
+        r -= c;
+    }
+    RVMC_DEV_ASSERT(r < h[d]);
+    return d;
+}
+
+__global__ void __launch_bounds__(STATS_THREADS, 3) point_stats_kernel(StatsArgs a) {
+    // dynamic shared memory (STATS_SMEM_BYTES, 70 KB => 3 blocks per SM); region A is the 4096-bin
+    // histogram of pass 0, then the per-group histograms of passes 1 and 2
+    extern __shared__ __align__(16) unsigned char stats_smem[];
+    unsigned int* histA = reinterpret_cast<unsigned int*>(stats_smem);           // [10 << 10]  40 KB
+    unsigned int* mode_hist = histA + (STATS_TARGETS << STATS_B1);               // [4096]      16 KB
+    signed char* table0 = reinterpret_cast<signed char*>(mode_hist + STATS_MODE_BINS_MAX);   // top-12 prefix -> group / -1
+    signed char* table1 = table0 + (1 << STATS_B0);                              // (group, middle digit) -> group2 / -1
     __shared__ double red[STATS_THREADS / 32];
     __shared__ unsigned int prefix[STATS_TARGETS];      // selected high bits so far, per target
     __shared__ unsigned int rank[STATS_TARGETS];        // rank still to find inside the prefix
-    __shared__ int group_of[STATS_TARGETS];             // histogram shared by equal prefixes
-    __shared__ unsigned int group_prefix[STATS_TARGETS];
-    __shared__ int n_groups;
+    __shared__ int group_of[STATS_TARGETS];
+    __shared__ int group0_of[STATS_TARGETS];
     __shared__ unsigned int max_bits;
 
     const int64_t n = a.n_real;
-    const float* sig = a.sigma + (size_t)blockIdx.x * a.sigma_stride;
+    const float* __restrict__ sig = a.sigma + (size_t)blockIdx.x * a.sigma_stride;
     rvmc_point_stats* st = a.stats_out + blockIdx.x;
     const double qs[5] = {5.0, 16.0, 50.0, 84.0, 95.0};
 
     if (threadIdx.x < STATS_TARGETS) {
         const int t = threadIdx.x;
         const double pos = (qs[t >> 1] / 100.0) * (double)(n - 1);
-        int64_t lo = (int64_t)floor(pos);
-        int64_t k = (t & 1) ? min(lo + 1, n - 1) : lo;
+        const int64_t lo = (int64_t)floor(pos);
+        rank[t] = (unsigned int)((t & 1) ? min(lo + 1, n - 1) : lo);
         prefix[t] = 0;
-        rank[t] = (unsigned int)k;
-        group_of[t] = 0;
     }
-    if (threadIdx.x == 0) {
-        n_groups = 1;
-        group_prefix[0] = 0;
-        max_bits = 0;
+    if (threadIdx.x == 0) max_bits = 0;
+    for (int i = threadIdx.x; i < (1 << STATS_B0); i += blockDim.x) {
+        histA[i] = 0;
+        table0[i] = -1;
     }
     for (int i = threadIdx.x; i < STATS_MODE_BINS_MAX; i += blockDim.x) mode_hist[i] = 0;
+    for (int i = threadIdx.x; i < (STATS_TARGETS << STATS_B1); i += blockDim.x) table1[i] = -1;
+    __syncthreads();
 
+    // four independent loads in flight per thread
+    auto for_each = [&](auto visit) {
+        int64_t i = threadIdx.x;
+        for (; i + 3 * (int64_t)blockDim.x < n; i += 4 * (int64_t)blockDim.x) {
+            const float x0 = __ldg(sig + i), x1 = __ldg(sig + i + blockDim.x), x2 = __ldg(sig + i + 2 * blockDim.x),
+                        x3 = __ldg(sig + i + 3 * blockDim.x);
+            visit(x0);
+            visit(x1);
+            visit(x2);
+            visit(x3);
+        }
+        for (; i < n; i += blockDim.x) visit(__ldg(sig + i));
+    };
+
+    // ---- pass 0: top 12 bits, sum, max ----------------------------------------------------------------
     double sum = 0.0;
-    unsigned int mx = 0;
-    int nb_mode = 0;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        for (int i = threadIdx.x; i < STATS_TARGETS * 256; i += blockDim.x) (&hist[0][0])[i] = 0;
-        __syncthreads();
-        const int ng = n_groups;
-        const bool do_mode = (pass == 1) && nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX;
+    {
+        unsigned int mx = 0, run_digit = 0xffffffffu, run_count = 0;
+        for_each([&](float x) {
+            const unsigned int bits = __float_as_uint(x);
+            const unsigned int digit = bits >> (32 - STATS_B0);
+            sum += (double)x;
+            mx = max(mx, bits);
+            if (digit != run_digit) {
+                if (run_count) atomicAdd(&histA[run_digit], run_count);
+                run_digit = digit;
+                run_count = 0;
+            }
+            ++run_count;
+        });
+        if (run_count) atomicAdd(&histA[run_digit], run_count);
+        atomicMax(&max_bits, mx);
+    }
+    sum = block_sum_f64(sum, red);       // contains the barriers
+    const double smax = (double)__uint_as_float(max_bits);
+    // len(np.arange(0, max+bin, bin)) - 1 bins
+    const double nbd = ceil((smax + a.bin) / a.bin) - 1.0;
+    const int nb_mode = (nbd >= 1.0) ? (nbd < 2.0e9 ? (int)nbd : 2000000000) : 0;   // NaN sigma -> no histogram
+    if (threadIdx.x < STATS_TARGETS) {
+        const int t = threadIdx.x;
+        unsigned int r = rank[t];
+        prefix[t] = locate_digit(histA, 1 << STATS_B0, r);
+        rank[t] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ng = 0;
+        for (int t = 0; t < STATS_TARGETS; ++t) {
+            if (table0[prefix[t]] < 0) table0[prefix[t]] = (signed char)ng++;
+            group0_of[t] = table0[prefix[t]];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (STATS_TARGETS << STATS_B1); i += blockDim.x) histA[i] = 0;
+    __syncthreads();
+
+    // ---- pass 1: middle 10 bits of the candidates + the mode histogram -----------------------------------
+    {
+        const bool do_mode = nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX;
         const double last_edge = (double)nb_mode * a.bin;
         const float inv_bin = (float)(1.0 / a.bin);
-        // pass 0 run-length cache: nearly every element shares its top byte, so a thread flushes a
-        // counter to the shared histogram only when the byte changes
-        unsigned int run_digit = 0xffffffffu, run_count = 0;
-        auto visit = [&](float x) {
+        for_each([&](float x) {
             const unsigned int bits = __float_as_uint(x);
-            const unsigned int digit = (bits >> shift) & 255u;
-            if (pass == 0) {
-                sum += (double)x;
-                mx = max(mx, bits);
-                if (digit != run_digit) {
-                    if (run_count) atomicAdd(&hist[0][run_digit], run_count);
-                    run_digit = digit;
-                    run_count = 0;
-                }
-                ++run_count;
-            } else {
-                const unsigned int high = bits >> (shift + 8);
-                for (int g = 0; g < ng; ++g)
-                    if (high == group_prefix[g]) atomicAdd(&hist[g][digit], 1u);
-            }
+            const int g = table0[bits >> (32 - STATS_B0)];
+            if (g >= 0) atomicAdd(&histA[(g << STATS_B1) + ((bits >> STATS_B2) & ((1u << STATS_B1) - 1u))], 1u);
             if (do_mode) {
                 // edges are k*bin (np.arange(0, max+bin, bin)); bin k = [k*bin, (k+1)*bin), the last
                 // bin is closed on the right (np.histogram).  fp32 guess, exact fp64 correction.
@@ -489,59 +549,46 @@ __global__ void __launch_bounds__(STATS_THREADS) point_stats_kernel(StatsArgs a)
                 RVMC_DEV_ASSERT(k >= -1 && k <= nb_mode);
                 if (k >= 0 && k < nb_mode) atomicAdd(&mode_hist[k], 1u);
             }
-        };
-        // four independent loads in flight per thread
-        int64_t i = threadIdx.x;
-        for (; i + 3 * (int64_t)blockDim.x < n; i += 4 * (int64_t)blockDim.x) {
-            const float x0 = __ldg(sig + i), x1 = __ldg(sig + i + blockDim.x), x2 = __ldg(sig + i + 2 * blockDim.x),
-                        x3 = __ldg(sig + i + 3 * blockDim.x);
-            visit(x0);
-            visit(x1);
-            visit(x2);
-            visit(x3);
-        }
-        for (; i < n; i += blockDim.x) visit(__ldg(sig + i));
-        if (pass == 0 && run_count) atomicAdd(&hist[0][run_digit], run_count);
-        if (pass == 0) {
-            atomicMax(&max_bits, mx);
-            sum = block_sum_f64(sum, red);       // contains the barriers
-            const double smax = (double)__uint_as_float(max_bits);
-            // len(np.arange(0, max+bin, bin)) - 1 bins
-            const double nbd = ceil((smax + a.bin) / a.bin) - 1.0;
-            nb_mode = (nbd >= 1.0) ? (nbd < 2.0e9 ? (int)nbd : 2000000000) : 0;   // NaN sigma -> no histogram
-        }
-        __syncthreads();
-        // locate each target's digit: thread t scans its group's 256 counters
-        if (threadIdx.x < STATS_TARGETS) {
-            const int t = threadIdx.x;
-            const unsigned int* h = hist[group_of[t]];
-            unsigned int r = rank[t], d = 0;
-            for (; d < 255; ++d) {
-                const unsigned int c = h[d];
-                if (r < c) break;
-                r -= c;
-            }
-            RVMC_DEV_ASSERT(d <= 255 && r < h[d]);          // the target rank lies inside the located digit
-            rank[t] = r;
-            prefix[t] = (prefix[t] << 8) | d;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int ngn = 0;
-            for (int t = 0; t < STATS_TARGETS; ++t) {
-                int g = -1;
-                for (int k = 0; k < ngn; ++k)
-                    if (group_prefix[k] == prefix[t]) g = k;
-                if (g < 0) {
-                    g = ngn++;
-                    group_prefix[g] = prefix[t];
-                }
-                group_of[t] = g;
-            }
-            n_groups = ngn;
-        }
-        __syncthreads();
+        });
     }
+    __syncthreads();
+    if (threadIdx.x < STATS_TARGETS) {
+        const int t = threadIdx.x;
+        unsigned int r = rank[t];
+        const unsigned int d = locate_digit(histA + (group0_of[t] << STATS_B1), 1 << STATS_B1, r);
+        rank[t] = r;
+        prefix[t] = (prefix[t] << STATS_B1) | d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ng = 0;
+        for (int t = 0; t < STATS_TARGETS; ++t) {
+            const int slot = (group0_of[t] << STATS_B1) + (int)(prefix[t] & ((1u << STATS_B1) - 1u));
+            if (table1[slot] < 0) table1[slot] = (signed char)ng++;
+            group_of[t] = table1[slot];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (STATS_TARGETS << STATS_B2); i += blockDim.x) histA[i] = 0;
+    __syncthreads();
+
+    // ---- pass 2: last 10 bits of the few remaining candidates ------------------------------------------
+    for_each([&](float x) {
+        const unsigned int bits = __float_as_uint(x);
+        const int g0 = table0[bits >> (32 - STATS_B0)];
+        if (g0 >= 0) {
+            const int g = table1[(g0 << STATS_B1) + ((bits >> STATS_B2) & ((1u << STATS_B1) - 1u))];
+            if (g >= 0) atomicAdd(&histA[(g << STATS_B2) + (bits & ((1u << STATS_B2) - 1u))], 1u);
+        }
+    });
+    __syncthreads();
+    if (threadIdx.x < STATS_TARGETS) {
+        const int t = threadIdx.x;
+        unsigned int r = rank[t];
+        const unsigned int d = locate_digit(histA + (group_of[t] << STATS_B2), 1 << STATS_B2, r);
+        prefix[t] = (prefix[t] << STATS_B2) | d;
+    }
+    __syncthreads();
 
     if (threadIdx.x == 0) {
         double pct[5];
@@ -560,7 +607,7 @@ __global__ void __launch_bounds__(STATS_THREADS) point_stats_kernel(StatsArgs a)
         st->p84 = pct[3];
         st->p95 = pct[4];
         st->mean = sum / (double)n;
-        st->sigma_max = (double)__uint_as_float(max_bits);
+        st->sigma_max = smax;
         st->n_hist_bins = (uint32_t)nb_mode;
         st->n_guard = 0;
         st->n_nonconverged = 0;
@@ -786,6 +833,8 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
     rc = cuda_status(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!rc) rc = cuda_status(cudaFuncSetAttribute(point_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   STATS_SMEM_BYTES), "point_stats_kernel smem");
     if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
     for (int k = 0; k < 2 && !rc; ++k)
         rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
@@ -811,7 +860,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         sa.hist_bins = hist_bins;
         sa.stats_out = stats_out + p0;
         sa.hist_out = hist_out ? hist_out + (size_t)p0 * hist_bins : nullptr;
-        point_stats_kernel<<<(unsigned int)np, STATS_THREADS, 0, side>>>(sa);
+        point_stats_kernel<<<(unsigned int)np, STATS_THREADS, STATS_SMEM_BYTES, side>>>(sa);
         rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
         if (!rc) rc = cuda_status(cudaEventRecord(ev_stats[half], side), "cudaEventRecord");
     }
@@ -901,6 +950,8 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
     rc = cuda_status(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!rc) rc = cuda_status(cudaFuncSetAttribute(point_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   STATS_SMEM_BYTES), "point_stats_kernel smem");
     if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
     for (int k = 0; k < 2 && !rc; ++k)
         rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
@@ -951,7 +1002,7 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
         sa.hist_bins = hist_bins;
         sa.stats_out = stats_out + p0 * n_fbins;
         sa.hist_out = hist_out ? hist_out + (size_t)p0 * n_fbins * hist_bins : nullptr;
-        point_stats_kernel<<<(unsigned int)rows, STATS_THREADS, 0, side>>>(sa);
+        point_stats_kernel<<<(unsigned int)rows, STATS_THREADS, STATS_SMEM_BYTES, side>>>(sa);
         rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
         if (!rc) rc = cuda_status(cudaEventRecord(ev_stats[half], side), "cudaEventRecord");
     }

@@ -195,7 +195,7 @@ def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**
     bad = int(stats["reserved"].sum())
     if bad:
         raise NotImplementedError("%d grid points have sigma_1D histograms wider than the %d bins the statistics "
-                                  "kernel holds; use a larger `bin`" % (bad, 8192))
+                                  "kernel holds; use a larger `bin`" % (bad, 4096))
     return out
 
 
@@ -264,7 +264,7 @@ def run_points_fbins(pops, seeds, fbins, measured_errors, sample_size, number_of
     bad = int(stats_all["reserved"].sum())
     if bad:
         raise NotImplementedError("%d grid points have sigma_1D histograms wider than the %d bins the statistics "
-                                  "kernel holds; use a larger `bin`" % (bad, 8192))
+                                  "kernel holds; use a larger `bin`" % (bad, 4096))
     return dict(stats=stats_all, local=local, counters=dv.to_host(counters), sigma=sigma_all, hist=hist_all)
 
 
