@@ -33,6 +33,16 @@ __device__ __forceinline__ T group_sum(T x, int G) {
     return x;
 }
 
+// sigma from the pivot-shifted sums of one realization (shared by every reducer so that they all
+// round alike)
+template <typename T>
+__device__ __forceinline__ T sigma_from_sums(T s1, T s2, int S, int ddof) {
+    // S == ddof -> 0/0 = NaN like NumPy
+    T var = (s2 - s1 * s1 / (T)S) / (T)(S - ddof);
+    var = var < (T)0 ? (T)0 : var;       // rounding can leave -0.0...: keep sqrt real (NaN stays NaN)
+    return sqrt(var);
+}
+
 // value(l): velocity of tile slot l = r*S + j (a functor over shared memory); wts: [S] weights
 // 1/err^2 in shared memory or nullptr (unweighted); wsum: sum of the weights; out[r] receives sigma
 // of realization r.  All threads of the block must call this (it contains warp shuffles);
@@ -70,6 +80,10 @@ __device__ __forceinline__ void reduce_tile_sigma_fn(Value value, int nr, int S,
             s2 = group_sum(s2, G);
         }
         if (valid && gl == 0) {
+            if (!wts) {
+                out[r] = (OutT)sigma_from_sums<T>(s1, s2, S, ddof);
+                continue;
+            }
             T var;
             if (wts) {
                 // sum w (v - mu)^2 / sum w  with  mu = pivot + s1 / wsum            (RVMC.py:263-268);

@@ -19,6 +19,8 @@
 //   phase C  cluster_reduce.cuh: two-pass dispersion per realization by sub-warp groups.
 // Every value is a function of (seed, global slot index) only, so the result does not depend on
 // the tile size, the launch geometry or the GPU the tile ran on.  Per-star values never reach HBM.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -320,6 +322,44 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
     __syncthreads();
 
     // ---- phase C: one reduction per binary fraction -------------------------------------------------
+    if (a.G == 1 && !a.weighted) {
+        // small clusters (one thread per realization): eight fractions per sweep over the row, the
+        // accumulators of each in registers; same operations in the same order as the generic reducer
+        for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+            const int base = r * S;
+            for (int k0 = 0; k0 < fa.n_fbins; k0 += 8) {
+                float s1[8], s2[8], pivot[8];
+                uint32_t thr[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) thr[k] = (k0 + k < fa.n_fbins) ? fa.thresh[k0 + k] : 0u;
+                {
+                    const float nz = noise[base], both = nz + rv[base];
+                    const uint32_t c = coin[base];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        pivot[k] = c < thr[k] ? both : nz;
+                        s1[k] = 0.0f;
+                        s2[k] = 0.0f;
+                    }
+                }
+                for (int j = 0; j < S; ++j) {
+                    const float nz = noise[base + j], both = nz + rv[base + j];
+                    const uint32_t c = coin[base + j];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float d = (c < thr[k] ? both : nz) - pivot[k];
+                        s1[k] += d;
+                        s2[k] = fmaf(d, d, s2[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k0 + k < fa.n_fbins)
+                        a.sigma_out[(point * fa.n_fbins + k0 + k) * a.sigma_stride + r0 + r] =
+                            sigma_from_sums<float>(s1[k], s2[k], S, a.ddof);
+            }
+        }
+    } else
     for (int k = 0; k < fa.n_fbins; ++k) {
         const uint32_t thr = fa.thresh[k];
         reduce_tile_sigma_fn<float, float>(
@@ -777,10 +817,17 @@ int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const float* meas_
 }
 
 int rvmc_grid_scratch_slots(int device) {
-    // one launch pair (fused kernel + statistics kernel) per batch of this many points: four
-    // statistics blocks per SM keep every SM busy for two waves (148 SMs x 2 resident blocks)
+    // rows of sigma_1D the scratch holds; it is used as two halves (the statistics kernel of one
+    // batch overlaps the fused kernel of the next), so one statistics launch covers slots/2 rows:
+    // 592 blocks = 4 per SM.  RVMC_GRID_SCRATCH_SLOTS overrides it (tuning).
     (void)device;
-    return 592;
+    static int slots = 0;
+    if (slots == 0) {
+        const char* env = getenv("RVMC_GRID_SCRATCH_SLOTS");
+        int v = env ? atoi(env) : 0;
+        slots = (v >= 64 && v <= (1 << 20)) ? (v & ~1) : 1184;
+    }
+    return slots;
 }
 
 int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* meas_err, int sample_size,
