@@ -281,6 +281,32 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * units_per_step * e2e_steps / float(t.item())
 
+    # ---- second headline of BASELINE.json: grid points per second (configs[4]) ----------------------
+    grid_info = None
+    if not args.no_grid:
+        from rvmc_b200 import grid as rgrid
+        axes = dict(period_pi=np.linspace(-0.95, 0.5, 64), mass_ratio_kappa=np.linspace(-0.95, 1.0, 64),
+                    fbin=np.linspace(0.0625, 1, 16))
+        rgrid.grid_search({k: v[:4] for k, v in axes.items()}, number_of_samples=1000, seed=1, device=dev)
+        g_times = []
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            gres = rgrid.grid_search(axes, number_of_samples=10 ** 5, seed=2024, observed_sigma=25.0, device=dev)
+            barrier()
+            g_times.append(time.perf_counter() - t0)
+        tg = torch.tensor([min(g_times)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        npts = int(np.prod(gres["shape"]))
+        grid_info = {"workload": "findBestDistributions grid (BASELINE configs[4]): 64 x 64 x 16 (pi, kappa, fbin) x 10^5 "
+                                 "realizations x 12 stars (M17 errors), statistics + best fit; points dealt round-robin "
+                                 "to the ranks, 80-byte statistics all-gathered; f_bin axis evaluated in one pass",
+                     "points": npts, "seconds": float(tg.item()), "points_per_s": npts / float(tg.item()),
+                     "scaling": "strong", "timing": "host wall clock, barrier + synchronize on both sides, best of 3, "
+                                                    "max over ranks; includes building the grid and the host copy of "
+                                                    "the statistics",
+                     "best_index": list(gres["best_index"])}
     if rank == 0:
         peaks, peak_src = measured_peaks()
         launch_ms = float(np.mean(per_launch_ms))
@@ -340,7 +366,7 @@ def run_gpu_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "BiasCorr(...).calculate_radial_velocities(); get_detected_binaries()",
                         "detected_fraction": frac},
-                "gpu_launches": args.steps, "roofline": roof,
+                "gpu_launches": args.steps, "roofline": roof, "grid": grid_info,
                 "counters": {"binary_epoch_rvs": int(counters[0]), "detected": int(counters[1]),
                              "fp64_guard_lanes": int(counters[2]), "nonconverged": int(counters[3])}}
         if world == 1 and not args.no_cpu_baseline:
@@ -373,6 +399,7 @@ def main():
     ap.add_argument("--samples", type=int, default=10 ** 6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipe-peaks", action="store_true")
+    ap.add_argument("--no-grid", action="store_true", help="skip the secondary grid-points/s measurement")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/); "
                          "default: the full-size capture profiles/r01_biascorr_fused_fullsize_ncu.md")
