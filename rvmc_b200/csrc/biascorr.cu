@@ -23,7 +23,9 @@
 
 namespace rvmc {
 
+#ifndef BC_THREADS
 #define BC_THREADS 256
+#endif
 
 struct BcArgs {
     PopF32 P32;
@@ -72,8 +74,8 @@ __device__ __forceinline__ double bc_mass_f64(const PopF64& P, int mode, const d
 // Noise normals of epochs 4g..4g+3 of one binary.
 __device__ __forceinline__ void bc_noise4_f32(const PhiloxKey& K, uint64_t item, uint32_t stream, int g, float z[4]) {
     const u32x4 w = philox_block(K, item, stream, (uint32_t)g);
-    box_muller_f32(w.x, w.y, z[0], z[1]);
-    box_muller_f32(w.z, w.w, z[2], z[3]);
+    box_muller_noise_f32(w.x, w.y, z[0], z[1]);
+    box_muller_noise_f32(w.z, w.w, z[2], z[3]);
 }
 __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint32_t stream, int g, double z[4]) {
     const u32x4 w = philox_block(seed, item, stream, (uint32_t)g);
@@ -90,7 +92,9 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
 // Each thread walks a.spt samples of its star (1..8, chosen by the host so that the grid still
 // holds >= 8 blocks per SM), so the per-block prologue (epoch tables, pair thresholds, two barriers)
 // is amortised over BC_THREADS * spt binaries.  3 blocks/SM at <= 85 registers measured best.
-#define BC_MAX_SPT 8
+#ifndef BC_MAX_SPT
+#define BC_MAX_SPT 16
+#endif
 #ifndef BC_MIN_BLOCKS
 #define BC_MIN_BLOCKS 3
 #endif
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
         const float K = semi_amplitude_f32(a.P32, o);
         float sw, cw;
         sincos_turn(o.wturn, sw, cw);
+        const float Ksw = K * sw, Kcw = K * cw;
         const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
         const double c0 = quirk ? RVMC_TWO_PI * uphase : uphase;
 
@@ -218,11 +223,11 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
             }
             M = (float)M64;
             int g, b;
-            const float shape = kepler_shape_f32<ITERS, GUARD>(M, M64, neg, o.e, rome2, sw, cw, a.kepler_iters,
-                                                               a.P32.guard_amp, g, b);
+            // K is folded into the orientation terms (the shape is linear in sin/cos omega)
+            float rv = kepler_shape_f32<ITERS, GUARD>(M, M64, neg, o.e, rome2, Ksw, Kcw, a.kepler_iters,
+                                                      a.P32.guard_amp, g, b);
             my_guard += g;
             my_bad += b;
-            float rv = K * shape;
             if (noisy) rv = fmaf(err_s[k], z[k & 3], rv);
             rvs[k] = rv;
             vmax = fmaxf(vmax, rv);

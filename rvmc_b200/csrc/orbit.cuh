@@ -107,23 +107,29 @@ RVMC_HD float semi_amplitude_f32(const PopF32& P, const OrbitF32& o) {
 template <int ITERS = 0>
 RVMC_HD float kepler_f32(float M, float e, int iters_rt, float& sE, float& cE, float& resid) {
     const int iters = ITERS > 0 ? ITERS : iters_rt;      // ITERS > 0: fully unrolled, no loop overhead
-    const float pi = 3.14159265358979f;
+    // alpha = (3 pi^2 + 1.6 pi (pi - M)/(1+e)) / (pi^2 - 6) = a0 - a1 M.  Everything that depends on e
+    // alone (rc, a0, a1, ome2, ome3) is loop-invariant for a caller that solves several epochs of one
+    // orbit: the unrolled epoch loop of the multi-epoch kernel shares it.
     const float ome = 1.0f - e;
-    const float alpha = fmaf(5.026548245743669f * (pi - M), fast_rcp(1.0f + e), 29.608813203268074f) *
-                        0.25841921902300255f;     // (3 pi^2 + 1.6 pi (pi-M)/(1+e)) / (pi^2 - 6)
-    const float d = fmaf(3.0f, ome, alpha * e);
+    const float rc = fast_rcp(1.0f + e);
+    const float a1 = 1.2989824604108398f * rc;                        // 1.6 pi / (pi^2 - 6)
+    const float a0 = fmaf(4.080873754768689f, rc, 7.651638290191292f);   // 1.6 pi^2/(pi^2-6), 3 pi^2/(pi^2-6)
+    const float ome2 = ome + ome, ome3 = 3.0f * ome;
+    const float alpha = fmaf(-a1, M, a0);
+    const float d = fmaf(alpha, e, ome3);
     const float ad = alpha * d;
-    const float q = fmaf(2.0f * ad, ome, -M * M);
     const float M2 = M * M;
-    const float r = fmaf(3.0f * ad * (d - ome), M, M2 * M);
-    float w = fabsf(r) + fast_sqrt(fmaf(q * q, q, r * r));
-    w = fast_ex2(0.6666666666666666f * fast_lg2(w));             // w^(2/3)
+    const float q = fmaf(ad, ome2, -M2);
+    const float g = fmaf(3.0f, ad * fmaf(alpha, e, ome2), M2);       // r / M, with d - ome = 2 ome + alpha e
+    const float r = M * g;                                           // >= 0 for M >= 0
+    float w = r + fast_sqrt(fmaf(q * q, q, r * r));
+    w = fast_ex2(0.6666666666666666f * fast_lg2(w));                 // w^(2/3)
     const float den = fmaf(w, w + q, q * q);
-    // E0 = (2 r w / den + M) / d  with a single reciprocal
-    float E = fmaf(2.0f * r, w, M * den) * fast_rcp(den * d);
-    E = (M == 0.0f) ? 0.0f : E;                                   // 0/0 guard at the exact origin
+    // E0 = (2 r w / den + M) / d  with a single reciprocal.  At M = 0: r = 0, w = q > 0, den = 3 q^2 > 0
+    // for every e < 1, so E0 = 0 exactly and no 0/0 guard is needed.
+    float E = fmaf(r + r, w, M * den) * fast_rcp(den * d);
     float s, c, f = 0.0f;
-    sincos_rad(E, s, c);
+    sincos_0pi(E, s, c);
 #pragma unroll(ITERS > 0 ? ITERS : 1)
     for (int it = 0; it < iters; ++it) {
         f = fmaf(-e, s, E) - M;
@@ -132,7 +138,7 @@ RVMC_HD float kepler_f32(float M, float e, int iters_rt, float& sE, float& cE, f
         const float dE = -f * fp * fast_rcp(fmaf(fp, fp, -0.5f * f * fpp));
         E += dE;
         if (it + 1 < iters) {
-            sincos_rad(E, s, c);
+            sincos_0pi(E, s, c);
         } else {
             // sin/cos(E + dE) from sin/cos(E): |dE| < 1e-3 after the starter
             const float d2 = dE * dE;
@@ -163,10 +169,11 @@ RVMC_HD void kepler_refine_f64(double M, double e, double& E, double& sE, double
 // (cos nu = (cos E - e)/(1 - e cos E), sin nu = sqrt(1-e^2) sin E/(1 - e cos E)); equal to the
 // 2*atan(sqrt((1+e)/(1-e)) tan(E/2)) form of RVMC.py:211-212.  rome2 = sqrt(1 - e^2).
 RVMC_HD float rv_shape_f32(float e, float rome2, float sE, float cE, float sw, float cw) {
+    // shape = [ (cE - e) cw - sqrt(1-e^2) sE sw ] / (1 - e cE) + e cw; the products of per-orbit
+    // quantities (rome2 sw, e cw) are shared by all epochs of an orbit
     const float rd = fast_rcp(fmaf(-e, cE, 1.0f));
-    const float cnu = (cE - e) * rd;
-    const float snu = rome2 * sE * rd;
-    return fmaf(cnu, cw, fmaf(-snu, sw, e * cw));
+    const float B = rome2 * sw, C = e * cw;
+    return fmaf(rd, fmaf(-B, sE, fmaf(cE, cw, -C)), C);
 }
 
 // Kepler solve + shape for a mean anomaly of magnitude M in [0, pi] and sign `neg`

@@ -89,14 +89,49 @@ RVMC_HD void quadrant_fix(int q, float ss, float cc, float& s, float& c) {
     s = (q & 2) ? -a : a;
     c = ((q + 1) & 2) ? -b : b;
 }
+RVMC_HD uint32_t float_bits(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    union { float f; uint32_t u; } v;
+    v.f = x;
+    return v.u;
+#endif
+}
+// sin/cos of an angle in [0, pi] (slight excursions past either end are fine): the eccentric anomaly
+// of a mean anomaly folded into [0, pi].  Folded at pi/2 -- pi - E is exact in fp32 for E > pi/2
+// (Sterbenz) and the low word of pi restores the last bit -- then odd/even minimax polynomials on
+// [0, pi/2] (degree 9 / 10; 6.6e-9 relative / 2.7e-10 absolute before rounding, 1.3e-7 / 1.0e-7 in
+// fp32): sin keeps its RELATIVE accuracy towards both ends, where an error in E is amplified most
+// (periastron).  16 FMA-pipe instructions, nothing on the XU pipe, against 25 + FRND + F2I for the
+// general quadrant reduction.
+RVMC_HD void sincos_0pi(float E, float& s, float& c) {
+    const bool hi = E > 1.5707963267948966f;
+    const float y = hi ? (3.14159274101257324f - E) + -8.74227765734758577e-08f : E;
+    const float z = y * y;
+    float ps = fmaf(z, 2.6043765322843951e-06f, -1.9808937104531256e-04f);
+    ps = fmaf(z, ps, 8.3330565112898092e-03f);
+    ps = fmaf(z, ps, -1.6666659127902242e-01f);
+    s = fmaf(y * z, ps, y);
+    float pc = fmaf(z, -2.6063337837564222e-07f, 2.4761072372806247e-05f);
+    pc = fmaf(z, pc, -1.3888386773697650e-03f);
+    pc = fmaf(z, pc, 4.1666639349409541e-02f);
+    pc = fmaf(z, pc, -4.9999999513042248e-01f);
+    const float cy = fmaf(z, pc, 1.0f);
+    c = hi ? -cy : cy;
+}
 // sin/cos of 2*pi*t for a "turn" t (|t| small, e.g. a uniform draw): the quadrant split
 // t - k/4 is exact in fp32, so the reduced angle carries one rounding only.
 RVMC_HD void sincos_turn(float t, float& s, float& c) {
-    const float k = rintf(4.0f * t);
+    // round-to-nearest of 4t by the 1.5 * 2^23 shift: the quadrant lands in the low mantissa bits, so the
+    // rounding and the float->int conversion cost one FFMA + one FADD and no XU-pipe instruction
+    // (FRND / F2I share the 16-lane XU pipe with MUFU); valid for |4t| < 2^22
+    const float kb = fmaf(4.0f, t, 12582912.0f);
+    const float k = kb - 12582912.0f;
     const float r = fmaf(-0.25f, k, t) * 6.283185307179586f;
     float ss, cc;
     sincos_kernel(r, ss, cc);
-    quadrant_fix((int)k, ss, cc, s, c);
+    quadrant_fix((int)float_bits(kb), ss, cc, s, c);
 }
 // sin/cos of x radians for |x| up to a few pi (two-constant Cody-Waite reduction).
 RVMC_HD void sincos_rad(float x, float& s, float& c) {
@@ -173,6 +208,24 @@ RVMC_HD void box_muller_f32(uint32_t w1, uint32_t w2, float& z0, float& z1) {
     sincos_turn(u01_f32(w2), s, c);
     z0 = r * c;
     z1 = r * s;
+}
+// The measurement / cluster noise normals of the fused kernels: sin and cos of the uniform angle come
+// from MUFU.SIN / MUFU.COS (absolute error < 5e-7, i.e. < 3e-6 of the noise sigma -- six orders below
+// the Monte-Carlo scatter of any statistic of the noise), 4 instructions against 26 for the
+// polynomial pair.  The orbital angles keep the polynomial paths: they carry the 1e-5 parity bound.
+RVMC_HD void box_muller_noise_f32(uint32_t w1, uint32_t w2, float& z0, float& z1) {
+#if defined(__CUDA_ARCH__)
+    const float u1 = u01_open_f32(w1);
+    const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));   // sqrt(-2 ln u1)
+    const float th = (float)(w2 >> 8) * 3.7450702829239286e-07f;      // 2 pi u, u = (w2 >> 8) 2^-24
+    float s, c;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
+    z0 = r * c;
+    z1 = r * s;
+#else
+    box_muller_f32(w1, w2, z0, z1);
+#endif
 }
 RVMC_HD void box_muller_f64(uint32_t w1, uint32_t w2, double& z0, double& z1) {
     const double u1 = u01_open_f64(w1);

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
             const uint64_t pair = p_begin + pi;
             const u32x4 w = draw(pair, RVMC_STREAM_SLOT);
             float z0, z1;
-            box_muller_f32(w.z, w.w, z0, z1);
+            box_muller_noise_f32(w.z, w.w, z0, z1);
             const int64_t la = (int64_t)(2 * pair - slot0);
             l0 = (int)la;
             l1 = l0 + 1;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
             const uint64_t pair = p_begin + pi;
             const u32x4 w = philox_block(seed, pair, RVMC_STREAM_SLOT, 0);
             float z0, z1;
-            box_muller_f32(w.z, w.w, z0, z1);
+            box_muller_noise_f32(w.z, w.w, z0, z1);
             l0 = (int)(int64_t)(2 * pair - slot0);
             l1 = l0 + 1;
             RVMC_DEV_ASSERT(l0 >= -1 && l0 < nslots && l1 <= nslots);
@@ -385,7 +385,7 @@ __global__ void fused_trace_kernel(FusedPoint pt, const float* __restrict__ meas
         const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, 0);
         const u32x4 wb = philox_block(seed, slot, RVMC_STREAM_ORBIT_B, 0);
         float z0, z1;
-        box_muller_f32(ws.z, ws.w, z0, z1);
+        box_muller_noise_f32(ws.z, ws.w, z0, z1);
         const int odd = (int)(slot & 1);
         const int j = (int)(slot % (uint64_t)S);
         const float noise = (odd ? z1 : z0) * slot_scale(pt.pop.sigma_dyn, meas_err[j]);
