@@ -140,12 +140,11 @@ RVMC_HD float kepler_f32(float M, float e, int iters_rt, float& sE, float& cE, f
         if (it + 1 < iters) {
             sincos_0pi(E, s, c);
         } else {
-            // sin/cos(E + dE) from sin/cos(E): |dE| < 1e-3 after the starter
-            const float d2 = dE * dE;
-            const float cd = fmaf(d2, fmaf(d2, 4.1666667e-2f, -0.5f), 1.0f);
-            const float sd = dE * fmaf(d2, -1.6666667e-1f, 1.0f);
-            const float s1 = fmaf(s, cd, c * sd);
-            c = fmaf(c, cd, -s * sd);
+            // sin/cos(E + dE) from sin/cos(E): |dE| < 1e-3 after the starter, so cos dE = 1 - dE^2/2 and
+            // sin dE = dE to 4e-14 and 2e-10 absolute
+            const float cd = fmaf(dE * dE, -0.5f, 1.0f);
+            const float s1 = fmaf(s, cd, c * dE);
+            c = fmaf(c, cd, -s * dE);
             s = s1;
         }
     }
