@@ -84,6 +84,17 @@ def to_host(tensor):
 
 
 _copy_streams = {}
+_side_streams = {}
+
+
+def side_stream(device):
+    """A second compute stream per device: independent launches (disjoint star ranges of one pass)
+    alternate between it and the current stream so that the tail of one overlaps the head of the next."""
+    t = torch()
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = t.cuda.Stream(device=device)
+    return _side_streams[key]
 
 
 def to_host_overlapped(tensor, chunks):

@@ -33,6 +33,8 @@ class BiasCorr(dv.LazyArrays):
     of binaries (GPU implementation of RVMC_bias_corr.py:22-476)."""
 
     _ARRAY_ATTRS = _ORBIT + ("semi_major_axis", "max_orbital_velocity", "delta_rv", "delta_rv_single")
+    # star ranges a large fused pass is launched in (the D2H copy of one range overlaps the next ranges)
+    _d2h_chunks = 12
 
     def __init__(self, t_obs, masses=None, mass_errors=None, number_of_samples=10**4, min_mass=6,
                  max_mass=20, min_period=10**0.15, max_period=10**3.5, period_pi=-0.5, mass_ratio_kappa=0,
@@ -190,15 +192,26 @@ class BiasCorr(dv.LazyArrays):
     def _tables(self):
         """Device tables of the observing campaign: n_epochs[nstars], t_obs / rv_err [nstars][max_epochs]."""
         nstars = self.number_of_stars
-        nep = np.array([len(np.ravel(t)) for t in self.t_obs], dtype=np.int32)
+        rows = [np.ravel(t) for t in self.t_obs]
+        nep = np.fromiter((r.size for r in rows), dtype=np.int32, count=nstars)
         if nstars and nep.min() < 1:
             raise ValueError("every star needs at least one observing epoch")
         max_ep = int(nep.max()) if nstars else 1
-        tob = np.zeros((nstars, max_ep), dtype=np.float64)
-        for i, t in enumerate(self.t_obs):
-            tob[i, :nep[i]] = np.ravel(t)
+        ragged = bool(nstars) and int(nep.min()) != max_ep
+        if nstars and not ragged:
+            tob = np.array(rows, dtype=np.float64)
+        else:
+            tob = np.zeros((nstars, max_ep), dtype=np.float64)
+            for i, r in enumerate(rows):
+                tob[i, :nep[i]] = r
         err = None
-        if self.__dict__.get("rv_errors", None) is not None:
+        rv_errors = self.__dict__.get("rv_errors", None)
+        if rv_errors is not None and not isinstance(rv_errors, (np.ndarray, list)):
+            # one scalar for every star and epoch (check_error_shape's last branch, :391-392)
+            err = np.full((nstars, max_ep), rv_errors, dtype=np.float32)
+            if ragged:
+                err[np.arange(max_ep)[None, :] >= nep[:, None]] = 0.0
+        elif rv_errors is not None:
             err = np.zeros((nstars, max_ep), dtype=np.float32)
             for i in range(nstars):
                 self.current_star = i
@@ -439,38 +452,81 @@ class BiasCorr(dv.LazyArrays):
         counters = dv.zeros((4,), "int64", dev)
         per_star = dv.zeros((max(nstars, 1),), "int32", dev)
         # large problems go out as a few launches over star ranges: the copy of one range's results
-        # to the host (get_detected_binaries) then overlaps the compute of the next ranges
-        n_chunks = min(nstars, 8) if nstars * ns >= 4_000_000 else 1
-        bounds = np.linspace(0, nstars, max(n_chunks, 1) + 1).astype(int)
+        # to the host (get_detected_binaries) then overlaps the compute of the next ranges.  The
+        # ranges taper (each about 0.7 of the previous one) so that the last copy, which nothing
+        # overlaps, is small; everything launch-invariant is prepared once.
+        if nstars * ns >= 4_000_000 and nstars > 1:
+            n_chunks = min(nstars, self._d2h_chunks)
+            w = 0.7 ** np.arange(n_chunks)
+            bounds = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * nstars)]).astype(int)
+        else:
+            bounds = np.array([0, nstars])
         chunks = []
         t = dv.torch()
-        for s0, s1 in zip(bounds[:-1], bounds[1:]):
-            if s1 > s0:
-                self._launch_fused(nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, None, counters,
-                                   per_star, stars=(int(s0), int(s1)))
-                ev = t.cuda.Event()
-                ev.record(t.cuda.current_stream(dev))
-                chunks.append((int(s0), int(s1), ev))
+        launch = self._fused_launcher(max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, None, counters,
+                                      per_star)
+        # the ranges are independent: they alternate between the current stream and a side stream, so the
+        # draining tail of one launch is filled by the first blocks of the next
+        main = t.cuda.current_stream(dev)
+        streams = [main, dv.side_stream(dev)] if len(bounds) > 2 else [main]
+        if len(streams) > 1:
+            ready = t.cuda.Event()
+            ready.record(main)
+            streams[1].wait_event(ready)
+        with dv.DeviceGuard(dev):
+            for k, (s0, s1) in enumerate(zip(bounds[:-1], bounds[1:])):
+                if s1 > s0:
+                    st = streams[k % len(streams)]
+                    launch(int(s0), int(s1), C.c_void_p(st.cuda_stream))
+                    ev = t.cuda.Event()
+                    ev.record(st)
+                    chunks.append((int(s0), int(s1), ev))
+        if len(streams) > 1:
+            done = t.cuda.Event()
+            done.record(streams[1])
+            main.wait_event(done)        # later work on the current stream sees every range
         self._rv_cache = dict(mode="fused", nep=nep, max_ep=max_ep, d_nep=d_nep, d_tobs=d_tobs, d_err=d_err,
                               det={(float(delta_RV), float(n_sigma_RV)): (det, chunks)} if det is not None else {},
                               counters=counters, per_star=per_star)
         self._set_device("delta_rv", drv)
 
-    def _launch_fused(self, nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
-                      per_star, stars=None):
+    def _fused_launcher(self, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
+                        per_star):
+        """-> launch(s0, s1): one rvmc_biascorr_fused call over stars [s0, s1).  Population, mass tables
+        and base pointers are resolved once; a star range is pointer arithmetic on the row-major
+        [nstars, ...] buffers (the caller holds the device guard)."""
         dev = self._device
         ns = int(self.number_of_samples)
-        s0, s1 = (0, self.number_of_stars) if stars is None else stars
         m, me = self._mass_tables()
+        pop = self._pop()
+        lib = _abi.lib()
+        quirk = 0 if self.physical_phase else 1
+        stream = dv.stream_ptr(dev)
+        keep = (d_nep, d_tobs, d_err, m, me, drv, det, rv_out, counters, per_star, pop)
 
-        def rows(x):
-            return None if x is None else x[s0:s1]
-        with dv.DeviceGuard(dev):
-            _abi.check(_abi.lib().rvmc_biascorr_fused(
-                C.byref(self._pop()), self._seed0, self._rv_seed, s0, s1 - s0, max_ep, dv.ptr(rows(d_nep)),
-                dv.ptr(rows(d_tobs)), dv.ptr(rows(d_err)), self._mass_mode, dv.ptr(rows(m)), dv.ptr(rows(me)),
-                0 if self.physical_phase else 1, float(delta_RV), float(n_sigma_RV), 0, ns, ns, dv.ptr(rows(drv)),
-                dv.ptr(rows(det)), dv.ptr(rows(rv_out)), dv.ptr(counters), dv.ptr(rows(per_star)), dv.stream_ptr(dev)))
+        def base(x):
+            return (0, 0) if x is None else (x.data_ptr(), x.stride(0) * x.element_size() if x.dim() else 0)
+        b_nep, b_tobs, b_err, b_m, b_me = base(d_nep), base(d_tobs), base(d_err), base(m), base(me)
+        b_drv, b_det, b_rv, b_star = base(drv), base(det), base(rv_out), base(per_star)
+        p_cnt = dv.ptr(counters)
+        args = (float(delta_RV), float(n_sigma_RV))
+
+        def rows(b, s0):
+            return (b[0] + s0 * b[1]) if b[0] else None
+
+        def launch(s0, s1, stream=stream, _keep=keep):
+            _abi.check(lib.rvmc_biascorr_fused(
+                C.byref(pop), self._seed0, self._rv_seed, s0, s1 - s0, max_ep, rows(b_nep, s0), rows(b_tobs, s0),
+                rows(b_err, s0), self._mass_mode, rows(b_m, s0), rows(b_me, s0), quirk, args[0], args[1], 0, ns, ns,
+                rows(b_drv, s0), rows(b_det, s0), rows(b_rv, s0), p_cnt, rows(b_star, s0), stream))
+        return launch
+
+    def _launch_fused(self, nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
+                      per_star, stars=None):
+        s0, s1 = (0, self.number_of_stars) if stars is None else stars
+        with dv.DeviceGuard(self._device):
+            self._fused_launcher(max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
+                                 per_star)(int(s0), int(s1))
 
     def _radial_velocities_list(self):
         """`radial_velocities`: list of (n_epochs_i, n_samples) arrays (RVMC_bias_corr.py:250,419-421)."""
