@@ -34,13 +34,29 @@ __device__ __forceinline__ T group_sum(T x, int G) {
 }
 
 // sigma from the pivot-shifted sums of one realization (shared by every reducer so that they all
-// round alike)
+// round alike).  The divisors enter as reciprocals computed once per thread (inv_S = 1/S,
+// inv_dof = 1/(S - ddof); S == ddof -> 0 * inf = NaN like NumPy's 0/0): fp64 -- the finite-pool path
+// that follows the reference to 1e-12 -- keeps true divisions and the IEEE square root, fp32 uses
+// the reciprocals and MUFU.SQRT (2 ulp; the fused path's sigma carries 1e-5 anyway).
 template <typename T>
-__device__ __forceinline__ T sigma_from_sums(T s1, T s2, int S, int ddof) {
-    // S == ddof -> 0/0 = NaN like NumPy
-    T var = (s2 - s1 * s1 / (T)S) / (T)(S - ddof);
-    var = var < (T)0 ? (T)0 : var;       // rounding can leave -0.0...: keep sqrt real (NaN stays NaN)
+struct SigmaNorm {
+    T S, dof, inv_S, inv_dof;
+    __device__ __forceinline__ SigmaNorm(int S_, int ddof) : S((T)S_), dof((T)(S_ - ddof)) {
+        inv_S = (T)1 / S;
+        inv_dof = (T)1 / dof;
+    }
+};
+__device__ __forceinline__ double sigma_from_sums(double s1, double s2, const SigmaNorm<double>& n) {
+    double var = (s2 - s1 * s1 / n.S) / n.dof;
+    var = var < 0.0 ? 0.0 : var;         // rounding can leave -0.0...: keep sqrt real (NaN stays NaN)
     return sqrt(var);
+}
+__device__ __forceinline__ float sigma_from_sums(float s1, float s2, const SigmaNorm<float>& n) {
+    float var = fmaf(-s1 * n.inv_S, s1, s2) * n.inv_dof;
+    var = var < 0.0f ? 0.0f : var;
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(var));
+    return r;
 }
 
 // value(l): velocity of tile slot l = r*S + j (a functor over shared memory); wts: [S] weights
@@ -54,6 +70,7 @@ __device__ __forceinline__ void reduce_tile_sigma_fn(Value value, int nr, int S,
     const int gi = threadIdx.x / G;
     const int gl = threadIdx.x & (G - 1);
     const int iters = (nr + ng - 1) / ng;
+    const SigmaNorm<T> norm(S, ddof);
     RVMC_DEV_ASSERT(G >= 1 && G <= 32 && (G & (G - 1)) == 0 && gl < G);
     for (int it = 0; it < iters; ++it) {
         const int r = it * ng + gi;
@@ -81,21 +98,15 @@ __device__ __forceinline__ void reduce_tile_sigma_fn(Value value, int nr, int S,
         }
         if (valid && gl == 0) {
             if (!wts) {
-                out[r] = (OutT)sigma_from_sums<T>(s1, s2, S, ddof);
+                out[r] = (OutT)sigma_from_sums(s1, s2, norm);
                 continue;
             }
-            T var;
-            if (wts) {
-                // sum w (v - mu)^2 / sum w  with  mu = pivot + s1 / wsum            (RVMC.py:263-268);
-                // ddof = 1 applies the Bessel-type factor S/(S-1) of the variant the reference keeps
-                // commented out at RVMC.py:267
-                const T m = s1 / wsum;
-                var = s2 / wsum - m * m;
-                if (ddof) var = var * (T)S / (T)(S - ddof);
-            } else {
-                // S == ddof -> 0/0 = NaN like NumPy
-                var = (s2 - s1 * s1 / (T)S) / (T)(S - ddof);
-            }
+            // sum w (v - mu)^2 / sum w  with  mu = pivot + s1 / wsum            (RVMC.py:263-268);
+            // ddof = 1 applies the Bessel-type factor S/(S-1) of the variant the reference keeps
+            // commented out at RVMC.py:267
+            const T m = s1 / wsum;
+            T var = s2 / wsum - m * m;
+            if (ddof) var = var * (T)S / (T)(S - ddof);
             var = var < (T)0 ? (T)0 : var;       // rounding can leave -0.0...: keep sqrt real (NaN stays NaN)
             out[r] = (OutT)sqrt(var);
         }

@@ -323,41 +323,46 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
 
     // ---- phase C: one reduction per binary fraction -------------------------------------------------
     if (a.G == 1 && !a.weighted) {
-        // small clusters (one thread per realization): eight fractions per sweep over the row, the
-        // accumulators of each in registers; same operations in the same order as the generic reducer
-        for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        // small clusters: a work item is (realization, group of eight fractions) -- one sweep over the row
+        // with the eight accumulator pairs in registers; same operations in the same order as the generic
+        // reducer.  Items are dealt group-major, so a warp holds 32 consecutive realizations of one group
+        // (coalesced stores); the host sizes the tile so that the items fill the block's threads.
+        const int ngroups = (fa.n_fbins + 7) >> 3;
+        const SigmaNorm<float> norm(S, a.ddof);
+        for (int item = threadIdx.x; item < nr * ngroups; item += blockDim.x) {
+            const int grp = item / nr;
+            const int r = item - grp * nr;
+            const int k0 = grp << 3;
             const int base = r * S;
-            for (int k0 = 0; k0 < fa.n_fbins; k0 += 8) {
-                float s1[8], s2[8], pivot[8];
-                uint32_t thr[8];
+            float s1[8], s2[8], pivot[8];
+            uint32_t thr[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) thr[k] = (k0 + k < fa.n_fbins) ? fa.thresh[k0 + k] : 0u;
-                {
-                    const float nz = noise[base], both = nz + rv[base];
-                    const uint32_t c = coin[base];
+            for (int k = 0; k < 8; ++k) thr[k] = (k0 + k < fa.n_fbins) ? fa.thresh[k0 + k] : 0u;
+            {
+                const float nz = noise[base], both = nz + rv[base];
+                const uint32_t c = coin[base];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        pivot[k] = c < thr[k] ? both : nz;
-                        s1[k] = 0.0f;
-                        s2[k] = 0.0f;
-                    }
+                for (int k = 0; k < 8; ++k) {
+                    pivot[k] = c < thr[k] ? both : nz;
+                    s1[k] = 0.0f;
+                    s2[k] = 0.0f;
                 }
-                for (int j = 0; j < S; ++j) {
-                    const float nz = noise[base + j], both = nz + rv[base + j];
-                    const uint32_t c = coin[base + j];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float d = (c < thr[k] ? both : nz) - pivot[k];
-                        s1[k] += d;
-                        s2[k] = fmaf(d, d, s2[k]);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k0 + k < fa.n_fbins)
-                        a.sigma_out[(point * fa.n_fbins + k0 + k) * a.sigma_stride + r0 + r] =
-                            sigma_from_sums<float>(s1[k], s2[k], S, a.ddof);
             }
+            for (int j = 0; j < S; ++j) {
+                const float nz = noise[base + j], both = nz + rv[base + j];
+                const uint32_t c = coin[base + j];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float d = (c < thr[k] ? both : nz) - pivot[k];
+                    s1[k] += d;
+                    s2[k] = fmaf(d, d, s2[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k0 + k < fa.n_fbins)
+                    a.sigma_out[(point * fa.n_fbins + k0 + k) * a.sigma_stride + r0 + r] =
+                        sigma_from_sums(s1[k], s2[k], norm);
         }
     } else
     for (int k = 0; k < fa.n_fbins; ++k) {
@@ -978,8 +983,17 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
     const FusedPoint* d_points = (const FusedPoint*)ws;
 
     const int S = sample_size;
-    const int T = 2048;
-    const int R = T / S;
+    // Tile height: up to 3072 slots, and -- for the small clusters whose phase C runs one thread per
+    // (realization, group of eight fractions) -- a multiple of what makes those items fill whole
+    // passes of the 256 threads (S = 12, 16 fractions: R = 256, 512 items, two full passes).
+    int R = 3072 / S;
+    {
+        const int ngroups = (n_fbins + 7) / 8;
+        int step = 256;
+        for (int g = ngroups; (g & 1) == 0 && step > 1; g >>= 1) step >>= 1;      // 256 / gcd(256, ngroups)
+        if (R >= step) R -= R % step;
+        if (R < 1) R = 1;
+    }
     const size_t slots = (size_t)R * S;
     const size_t smem = slots * (2 * sizeof(float) + sizeof(uint32_t) + sizeof(uint16_t)) + 2 * (size_t)S * sizeof(float) + 16;
     const int64_t tiles_per_point = (n_real + R - 1) / R;
