@@ -114,9 +114,11 @@ void hc_sincos_f64(int64_t n, const double* x, double* s, double* c) {
     for (int64_t i = 0; i < n; ++i) sincos_f64_bounded(x[i], s[i], c[i]);
 }
 
+// turn: 1 sincos_turn (angle in turns), 0 sincos_rad, 2 sincos_0pi (eccentric anomaly in [0, pi])
 void hc_sincos(int64_t n, const float* t, int turn, float* s, float* c) {
     for (int64_t i = 0; i < n; ++i) {
-        if (turn) sincos_turn(t[i], s[i], c[i]);
+        if (turn == 1) sincos_turn(t[i], s[i], c[i]);
+        else if (turn == 2) sincos_0pi(t[i], s[i], c[i]);
         else sincos_rad(t[i], s[i], c[i]);
     }
 }

@@ -175,6 +175,18 @@ def test_box_muller_and_sincos():
     lib.hc_sincos(C.c_int64(n), x.ctypes.data_as(C.c_void_p), 0, s.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p))
     assert np.max(np.abs(s - np.sin(x.astype(np.float64)))) < 2e-7
     assert np.max(np.abs(c - np.cos(x.astype(np.float64)))) < 2e-7
+    # the eccentric anomaly's own path: [0, pi] with the starter's slack past both ends; sin keeps its
+    # RELATIVE accuracy towards 0 and pi (periastron/apastron), cos its absolute accuracy
+    E = np.concatenate([rng.uniform(-1e-3, np.pi + 1e-3, n), rng.uniform(0, 1e-2, 2000), np.pi - rng.uniform(0, 1e-2, 2000),
+                        [0.0, np.pi / 2, np.float32(np.pi)]]).astype(np.float32)
+    s, c = np.empty(E.size, np.float32), np.empty(E.size, np.float32)
+    lib.hc_sincos(C.c_int64(E.size), E.ctypes.data_as(C.c_void_p), 2, s.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p))
+    E64 = E.astype(np.float64)
+    assert np.max(np.abs(c - np.cos(E64))) < 1.5e-7
+    assert np.max(np.abs(s - np.sin(E64))) < 1.5e-7
+    inner = (np.abs(E64) > 1e-6) & (np.abs(E64 - np.pi) > 1e-6)
+    assert np.max(np.abs(s[inner] / np.sin(E64[inner]) - 1)) < 2.5e-7
+    assert s[E == 0][0] == 0.0 and c[E == 0][0] == 1.0
 
 
 def test_exp10_fast_f64():

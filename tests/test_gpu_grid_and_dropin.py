@@ -96,6 +96,25 @@ def test_fbin_axis_in_one_pass_is_bit_identical_to_pointwise(S, weighted, ddof, 
     assert c["stats"].shape == (2, 40) and np.all(np.diff(c["stats"]["mean"], axis=1) >= -0.35)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,nf,n_real", [(12, 16, 1000), (12, 11, 700), (7, 24, 513), (3, 32, 2000), (16, 8, 300)])
+def test_fbin_axis_fraction_groups_and_tile_sizes(S, nf, n_real):
+    """Small clusters reduce one (realization, group of eight fractions) item per thread and the host
+    sizes the tile from (S, number of groups): every combination -- a partial last group, partial
+    last tiles, two to four groups -- must stay bit-identical to point-by-point evaluation."""
+    pops = grid.points_array(3, period_pi=[-0.5, 0.2, -0.9], mass_ratio_kappa=[0.0, 0.5, -0.5])
+    seeds = grid.point_seeds(99, 3)
+    fbins = np.linspace(0.03, 1.0, nf)
+    err = np.resize(M17, S)
+    a = grid.run_points_fbins(pops, seeds, fbins, err, S, n_real, keep_sigma=True, distributed=False)
+    exp = np.repeat(pops, nf)
+    exp["fbin"] = np.tile(fbins, 3)
+    b = grid.run_points(exp, np.repeat(seeds, nf), err, S, n_real, keep_sigma=True, distributed=False)
+    np.testing.assert_array_equal(a["sigma"].reshape(-1, n_real), b["sigma"])
+    for k in ("median", "mode", "mean", "p05", "p95"):
+        np.testing.assert_array_equal(a["stats"][k].ravel(), b["stats"][k], err_msg=k)
+
+
 def test_reference_entry_points_and_best_fit(tmp_path):
     t = grid.get_Pdistr_stats(measured_errors=M17, sample_size=12, pmin=1.4, pmax=3500, Npoints=12, bin=0.5, fbin=0.7,
                               min_mass=6, max_mass=20, number_of_samples=20000, seed=3)
@@ -294,6 +313,34 @@ def test_biascorr_class_fused_and_replay_modes():
     bc2.inclination = np.zeros((3, 20000))
     bc2.calculate_radial_velocities()
     assert bc2.get_detected_binaries().mean() < 1e-3
+
+
+@pytest.mark.gpu
+def test_biascorr_large_pass_in_star_ranges_equals_one_launch():
+    """Above 4e6 binaries the class launches the fused kernel over tapered star ranges on two
+    alternating streams and copies each range's flags to the host as it completes; the result must be
+    the same bits as one launch over all stars."""
+    days = np.array([0, 1, 7, 30, 180, 365.0]) * 86400.0
+    t_obs = [days + 3600.0 * i for i in range(9)]
+    errs = [1.0 + 0.25 * i for i in range(9)]
+    res = []
+    saved = BiasCorr._d2h_chunks
+    try:
+        for chunks in (1, 12, 4):
+            BiasCorr._d2h_chunks = chunks
+            bc = BiasCorr(t_obs, number_of_samples=500_000, rv_errors=errs, seed=11)
+            bc.calculate_radial_velocities()
+            det = bc.get_detected_binaries()
+            res.append((np.asarray(bc.delta_rv).copy(), det.copy(), bc.detection_counts()))
+    finally:
+        BiasCorr._d2h_chunks = saved
+    for drv, det, (per_star, counters) in res[1:]:
+        np.testing.assert_array_equal(drv, res[0][0])
+        np.testing.assert_array_equal(det, res[0][1])
+        np.testing.assert_array_equal(per_star, res[0][2][0])
+        assert counters == res[0][2][1]
+    assert res[0][1].shape == (9, 500_000) and res[0][2][1]["binary_epoch_rvs"] == 9 * 500_000 * 6
+    np.testing.assert_array_equal(res[0][2][0], res[0][1].sum(axis=1))
 
 
 def test_biascorr_constructor_errors_and_modes():
