@@ -93,6 +93,14 @@ def shard_indices(n_points, rank, world):
     return np.arange(rank, n_points, world, dtype=np.int64)
 
 
+def _records(byte_tensor):
+    """uint8 tensor holding rvmc_point_stats records -> writable NumPy structured array that owns its
+    memory (one device-to-host copy, no further host copies)."""
+    t = byte_tensor.detach()
+    host = t.cpu() if t.is_cuda else t.clone()
+    return host.numpy().view(STATS_DTYPE)
+
+
 def gather_point_stats(local_bytes, n_points, rank, world, group=None):
     """All-gather of the per-point statistics.  `local_bytes`: uint8 tensor [n_local*80] (CPU for
     gloo, CUDA for NCCL) holding this rank's rvmc_point_stats in shard order.  Returns a NumPy
@@ -100,14 +108,14 @@ def gather_point_stats(local_bytes, n_points, rank, world, group=None):
     import torch
     item = STATS_DTYPE.itemsize
     if world == 1:
-        return np.frombuffer(local_bytes.detach().cpu().numpy().tobytes(), dtype=STATS_DTYPE).copy()
+        return _records(local_bytes)
     import torch.distributed as dist
     n_max = (n_points + world - 1) // world
     pad = torch.zeros(n_max * item, dtype=torch.uint8, device=local_bytes.device)
     pad[:local_bytes.numel()] = local_bytes
     out = torch.empty(world * n_max * item, dtype=torch.uint8, device=local_bytes.device)
     dist.all_gather_into_tensor(out, pad, group=group)
-    raw = np.frombuffer(out.cpu().numpy().tobytes(), dtype=STATS_DTYPE).reshape(world, n_max)
+    raw = _records(out).reshape(world, n_max)
     res = np.empty(n_points, dtype=STATS_DTYPE)
     for r in range(world):
         idx = shard_indices(n_points, r, world)
@@ -273,14 +281,14 @@ def gather_point_stats_rows(local_bytes, n_points, row_len, rank, world, group=N
     import torch
     item = STATS_DTYPE.itemsize * row_len
     if world == 1:
-        return np.frombuffer(local_bytes.detach().cpu().numpy().tobytes(), dtype=STATS_DTYPE).reshape(n_points, row_len).copy()
+        return _records(local_bytes).reshape(n_points, row_len)
     import torch.distributed as dist
     n_max = (n_points + world - 1) // world
     pad = torch.zeros(n_max * item, dtype=torch.uint8, device=local_bytes.device)
     pad[:local_bytes.numel()] = local_bytes
     out = torch.empty(world * n_max * item, dtype=torch.uint8, device=local_bytes.device)
     dist.all_gather_into_tensor(out, pad, group=group)
-    raw = np.frombuffer(out.cpu().numpy().tobytes(), dtype=STATS_DTYPE).reshape(world, n_max, row_len)
+    raw = _records(out).reshape(world, n_max, row_len)
     res = np.empty((n_points, row_len), dtype=STATS_DTYPE)
     for r in range(world):
         idx = shard_indices(n_points, r, world)
