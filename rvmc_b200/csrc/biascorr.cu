@@ -311,7 +311,7 @@ static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
 
 template <int NE>
 static int bc_dispatch(BcArgs& a, bool guard, int64_t blocks_per_star, cudaStream_t stream) {
-    if constexpr (NE <= 8) {
+    if constexpr (NE <= 16) {
         const bool fast = a.rv_err != nullptr && a.rv_out == nullptr && a.kepler_iters == 1 && !guard &&
                           a.P64.logp.kind != POW_GENERAL;
         if (fast)
