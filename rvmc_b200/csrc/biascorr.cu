@@ -85,7 +85,7 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
 
 // NE    : compile-time bound on the epochs per star (<= 16: epoch loop fully unrolled, RVs in registers)
 // FAST  : the headline configuration with every launch-uniform switch resolved at compile time --
-//         measurement errors given, per-epoch RVs not written, one Halley step, fp64 guard proven
+//         measurement errors given, per-epoch RVs written only if RVOUT, one Halley step, fp64 guard proven
 //         unreachable by the host (guard_reachable()), period-law exponent 1 or 2, phase convention
 //         QUIRK.  !FAST keeps all of them as run-time values (same arithmetic, ~15 % more
 //         instructions, and a call to pow() for a general period-law exponent).
@@ -98,7 +98,7 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
 #ifndef BC_MIN_BLOCKS
 #define BC_MIN_BLOCKS 3
 #endif
-template <int NE, bool FAST, bool QUIRK>
+template <int NE, bool FAST, bool QUIRK, bool RVOUT>
 __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kernel(BcArgs a) {
     __shared__ double A_s[NE];            // 2 pi t_obs (quirk) or t_obs (physical)
     __shared__ float err_s[NE];
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
     RVMC_DEV_ASSERT(star >= 0 && star < a.nstars && ne >= 0 && ne <= NE && ne <= a.max_epochs);
     const bool noisy = FAST ? true : (a.rv_err != nullptr);
     const bool quirk = FAST ? QUIRK : (a.quirk_phase != 0);
-    float* const rv_out = FAST ? nullptr : a.rv_out;
+    float* const rv_out = (FAST && !RVOUT) ? nullptr : a.rv_out;
 
     if (threadIdx.x < ne) {
         const double t = a.t_obs[(size_t)star * a.max_epochs + threadIdx.x];
@@ -296,13 +296,13 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
     }
 }
 
-template <int NE, bool FAST, bool QUIRK>
+template <int NE, bool FAST, bool QUIRK, bool RVOUT>
 static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
     // gridDim.y carries the star (<= 65535 per launch)
     for (int s0 = 0; s0 < a.nstars; s0 += 65535) {
         a.star0 = s0;
         const int ny = a.nstars - s0 < 65535 ? a.nstars - s0 : 65535;
-        biascorr_fused_kernel<NE, FAST, QUIRK>
+        biascorr_fused_kernel<NE, FAST, QUIRK, RVOUT>
             <<<dim3((unsigned int)blocks_per_star, (unsigned int)ny), BC_THREADS, 0, stream>>>(a);
         RVMC_LAUNCH_CHECK();
     }
@@ -312,13 +312,15 @@ static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
 template <int NE>
 static int bc_dispatch(BcArgs& a, bool guard, int64_t blocks_per_star, cudaStream_t stream) {
     if constexpr (NE <= 16) {
-        const bool fast = a.rv_err != nullptr && a.rv_out == nullptr && a.kepler_iters == 1 && !guard &&
-                          a.P64.logp.kind != POW_GENERAL;
+        const bool fast = a.rv_err != nullptr && a.kepler_iters == 1 && !guard && a.P64.logp.kind != POW_GENERAL;
+        if (fast && a.rv_out)
+            return a.quirk_phase ? bc_launch<NE, true, true, true>(a, blocks_per_star, stream)
+                                 : bc_launch<NE, true, false, true>(a, blocks_per_star, stream);
         if (fast)
-            return a.quirk_phase ? bc_launch<NE, true, true>(a, blocks_per_star, stream)
-                                 : bc_launch<NE, true, false>(a, blocks_per_star, stream);
+            return a.quirk_phase ? bc_launch<NE, true, true, false>(a, blocks_per_star, stream)
+                                 : bc_launch<NE, true, false, false>(a, blocks_per_star, stream);
     }
-    return bc_launch<NE, false, false>(a, blocks_per_star, stream);
+    return bc_launch<NE, false, false, true>(a, blocks_per_star, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
