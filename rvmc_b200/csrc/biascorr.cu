@@ -175,9 +175,12 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
         // eccentricity regimes compare log10 P.
         double xd;
         if constexpr (FAST) {
-            // exponent 1 or 2 only (pi = 0 or the Sana et al. -0.5): no pow(), no call, no stack frame
+            // exponent 1 or 2 (pi = 0 or the Sana et al. -0.5) directly, any other by the call-free
+            // pow_bounded_f64: no pow(), no call, no stack frame
             const double p = __dadd_rn(a.P64.logp.a, __dmul_rn(a.P64.logp.b, u01_f64(wa.y)));
-            xd = ((a.P64.logp.kind == POW_ONE) ? p : p * p) * a.P64.logp.minv;
+            const double pw = (a.P64.logp.kind == POW_ONE) ? p
+                              : (a.P64.logp.kind == POW_TWO) ? p * p : pow_bounded_f64(p, a.P64.logp.inv);
+            xd = pw * a.P64.logp.minv;
         } else {
             xd = powerlaw_f64(a.P64.logp, u01_f64(wa.y));
         }
@@ -312,7 +315,7 @@ static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
 template <int NE>
 static int bc_dispatch(BcArgs& a, bool guard, int64_t blocks_per_star, cudaStream_t stream) {
     if constexpr (NE <= 16) {
-        const bool fast = a.rv_err != nullptr && a.kepler_iters == 1 && !guard && a.P64.logp.kind != POW_GENERAL;
+        const bool fast = a.rv_err != nullptr && a.kepler_iters == 1 && !guard;
         if (fast && a.rv_out)
             return a.quirk_phase ? bc_launch<NE, true, true, true>(a, blocks_per_star, stream)
                                  : bc_launch<NE, true, false, true>(a, blocks_per_star, stream);

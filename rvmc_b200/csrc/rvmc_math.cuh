@@ -172,11 +172,9 @@ RVMC_HD void sincos_f64_bounded(double x, double& s, double& c) {
     c = ((q + 1) & 2) ? -b : b;
 }
 
-// 10^y in fp64 for moderate |y| (|y| < ~300), relative error < 5e-14: y log2(10) = n + f with
-// |f| <= 0.5, 2^f by an 11th-degree Taylor polynomial in f ln 2, scaled by 2^n through the exponent
-// field.  ~18 instructions against ~50 for exp10(): the multi-epoch kernel needs 1/P to ~1e-10.
-RVMC_HD double exp10_fast_f64(double y) {
-    const double t = y * 3.3219280948873623479;           // log2(10)
+// 2^t in fp64 for moderate |t| (|t| < ~1000), relative error < 5e-14: t = n + f with |f| <= 0.5,
+// 2^f by an 11th-degree Taylor polynomial in f ln 2, scaled by 2^n through the exponent field.
+RVMC_HD double exp2_fast_f64(double t) {
     const double n = rint(t);
     const double g = (t - n) * 0.69314718055994530942;    // f ln 2, |g| <= 0.3466
     double p = 2.50521083854417187751e-08;                // 1/11!
@@ -195,6 +193,47 @@ RVMC_HD double exp10_fast_f64(double y) {
     return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
 #else
     return ldexp(p, (int)n);
+#endif
+}
+// 10^y, ~18 instructions against ~50 for exp10(): the multi-epoch kernel needs 1/P to ~1e-10.
+RVMC_HD double exp10_fast_f64(double y) { return exp2_fast_f64(y * 3.3219280948873623479); }   // log2(10)
+
+// p^y in fp64 for a positive NORMAL p (the argument of a power-law inverse CDF, bounded away from 0
+// and infinity by construction) and moderate |y log2 p|; relative error < 1e-13 |y|.  log2 p =
+// k + 2 atanh((m-1)/(m+1)) log2 e with m in [sqrt(1/2), sqrt 2); the reciprocal is two Newton steps
+// from MUFU.RCP, so there is no division, no libm call and no stack frame: the multi-epoch kernel
+// keeps its call-free instantiation for a general period-law exponent (RVMC_bias_corr.py:282-288
+// with pi not in {0, -0.5}).  ~55 instructions against a pow() call.
+RVMC_HD double pow_bounded_f64(double p, double y) {
+#if defined(__CUDA_ARCH__)
+    int hi = __double2hiint(p);
+    int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                    // m in [1, 2)
+    if (hi >= 0x3ff6a09e) {                                 // m >= ~sqrt 2: halve it
+        hi -= 0x00100000;
+        k += 1;
+    }
+    const double m = __hiloint2double(hi, __double2loint(p));
+    const double d = m + 1.0;
+    double r = (double)fast_rcp((float)d);
+    r = r * fma(-d, r, 2.0);
+    r = r * fma(-d, r, 2.0);
+    const double f = (m - 1.0) * r;
+    const double s = f * f;
+    double q = 1.0 / 19.0;
+    q = fma(q, s, 1.0 / 17.0);
+    q = fma(q, s, 1.0 / 15.0);
+    q = fma(q, s, 1.0 / 13.0);
+    q = fma(q, s, 1.0 / 11.0);
+    q = fma(q, s, 1.0 / 9.0);
+    q = fma(q, s, 1.0 / 7.0);
+    q = fma(q, s, 1.0 / 5.0);
+    q = fma(q, s, 1.0 / 3.0);
+    q = fma(q, s, 1.0);
+    const double l2 = fma(f * q, 2.8853900817779268147, (double)k);     // 2 log2(e) f q + k
+    return exp2_fast_f64(y * l2);
+#else
+    return pow(p, y);
 #endif
 }
 

@@ -113,6 +113,36 @@ def test_fused_multi_epoch_rv_matches_oracle_within_1e5(variant, quirk):
     assert res["cnt"][0] == ns * sum(len(t) for t in t_obs) and res["cnt"][3] == 0
 
 
+@pytest.mark.parametrize("quirk", [1, 0])
+@pytest.mark.parametrize("variant", [{}, dict(period_pi=-0.3, mass_ratio_kappa=-0.2, e_power=-0.4), dict(period_pi=0.37),
+                                     dict(period_pi=-0.95), dict(period_pi=0.0)])
+def test_compile_time_instantiation_matches_oracle_within_1e5(variant, quirk):
+    """The call-free instantiation the headline runs (errors given, one Halley step) with the per-epoch
+    RVs written out: vanishing errors make the noise term exactly negligible, so its orbital RVs face
+    the oracle directly -- including a general period-law exponent, which this instantiation takes
+    through pow_bounded_f64 (the phase needs the period to ~1e-9 relative here)."""
+    p = _abi.PopParams.defaults(**variant)
+    nstars, ns, seed, first = 2, 30000, 4242, 77
+    rng = np.random.RandomState(5)
+    t_obs = [DAYS6, np.sort(rng.uniform(0, np.pi * 1e7, 13))]          # 6 and 13 epochs: both unrolled variants
+    res = _fused(p, seed, 9, t_obs, [1e-30, 1e-30], ns, first=first, quirk=quirk)
+    for i in range(nstars):
+        o = orbits_from_draws(p, seed, biascorr_item(i, np.arange(first, first + ns)))
+        if quirk:
+            want = orc.multi_epoch_rv(t_obs[i], o["time"], o["period"], o["eccentricity"], o["mass_ratio"],
+                                      o["primary_mass"], o["inclination"], o["orbit_rotation"])
+        else:
+            tt = np.reshape(t_obs[i], (-1, 1)) + o["time"]
+            E = orc.kepler_exact(2 * np.pi * ((tt / o["period"]) % 1.0), o["eccentricity"])
+            a = orc.semi_major_axis(o["mass_ratio"], o["primary_mass"], o["period"])
+            vm = orc.max_orbital_velocity(o["mass_ratio"], o["primary_mass"], o["eccentricity"], a)
+            want = orc.binary_radial_velocity(vm, o["eccentricity"], o["inclination"], o["orbit_rotation"], E)
+        K = orc.semi_amplitude(o["mass_ratio"], o["primary_mass"], o["period"], o["eccentricity"], o["inclination"])
+        keep = ~near_regime_edge(o, 1e-9)
+        assert g.rel_err(res["rv"][i, :len(t_obs[i])], want, K)[:, keep].max() < 1e-5
+    assert res["cnt"][0] == ns * sum(len(t) for t in t_obs) and res["cnt"][2] == 0 and res["cnt"][3] == 0
+
+
 @pytest.mark.parametrize("errors", ["scalar", "per_epoch"])
 def test_fused_noise_and_detection_match_oracle(errors):
     p = _abi.PopParams.defaults()

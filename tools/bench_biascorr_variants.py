@@ -23,8 +23,9 @@ DAYS = np.array([0, 1, 7, 30, 180, 365.0, 400, 500, 730, 800, 900, 1000, 1100, 1
                  1900, 2000, 2100, 2200]) * 86400.0
 
 
-def run(name, nstars=100, ns=10 ** 6, ne=6, quirk=1, iters=1, uniform_err=True, mass_mode=0, rv_out=False, steps=10):
-    p = _abi.PopParams.defaults(kepler_iters=iters)
+def run(name, nstars=100, ns=10 ** 6, ne=6, quirk=1, iters=1, uniform_err=True, mass_mode=0, rv_out=False, steps=10,
+        **pop):
+    p = _abi.PopParams.defaults(kepler_iters=iters, **pop)
     d_nep = dv.to_device(np.full(nstars, ne, np.int32), "int32", dev)
     d_tobs = dv.to_device(np.tile(DAYS[:ne], (nstars, 1)), "float64", dev)
     err = np.full((nstars, ne), 2.0, np.float32)
@@ -61,6 +62,9 @@ run("per-epoch errors (15 pair tests)", uniform_err=False)
 run("two Halley steps (general instantiation)", iters=2)
 run("masses with errors (mass_mode 1)", mass_mode=1)
 run("per-epoch RVs written to HBM (2.4 GB)", rv_out=True, ns=10 ** 6)
+run("period_pi = -0.3 (general period-law exponent)", period_pi=-0.3)
+run("period_pi = 0 (flat in log P)", period_pi=0.0)
+run("kappa = -0.5, e_power = 0.3 (general q and e exponents)", mass_ratio_kappa=-0.5, e_power=0.3)
 run("8 epochs", ne=8, ns=750000)
 run("16 epochs", ne=16, ns=375000)
 run("24 epochs (run-time epoch loop)", ne=24, ns=250000)
