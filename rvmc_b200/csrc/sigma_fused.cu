@@ -262,6 +262,8 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
     const float invS = 1.0f / (float)S;
     const uint32_t thresh = fa.thresh_max;
     const int lane = threadIdx.x & 31;
+    // largest fraction = 1: every slot is a binary, the work queue is the identity and is skipped
+    const bool all_binaries = thresh >= (1u << 24);
 
     // ---- phase A: coins + noise (as sigma1d_fused_kernel, the coin itself is kept) ---------------
     const int npairs_pad = (npairs + 31) & ~31;
@@ -289,6 +291,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
                 bin1 = (w.y >> 8) < thresh;
             }
         }
+        if (all_binaries) continue;
         const unsigned m0 = __ballot_sync(0xffffffffu, bin0);
         const unsigned m1 = __ballot_sync(0xffffffffu, bin1);
         const int c0 = __popc(m0), c1 = __popc(m1);
@@ -303,10 +306,10 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
     __syncthreads();
 
     // ---- phase B: one orbit per slot that is a binary under the largest fraction -------------------
-    const int nq = qn;
+    const int nq = all_binaries ? nslots : qn;
     unsigned int my_guard = 0, my_bad = 0;
     for (int k = threadIdx.x; k < nq; k += blockDim.x) {
-        const int l = queue[k];
+        const int l = all_binaries ? k : queue[k];
         RVMC_DEV_ASSERT(l >= 0 && l < nslots);
         const uint64_t slot = slot0 + (uint64_t)l;
         const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, 0);
