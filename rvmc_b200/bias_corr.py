@@ -192,15 +192,25 @@ class BiasCorr(dv.LazyArrays):
     def _tables(self):
         """Device tables of the observing campaign: n_epochs[nstars], t_obs / rv_err [nstars][max_epochs]."""
         nstars = self.number_of_stars
-        rows = [np.ravel(t) for t in self.t_obs]
-        nep = np.fromiter((r.size for r in rows), dtype=np.int32, count=nstars)
+        tob = None
+        if nstars:
+            try:                                  # a regular campaign (same number of epochs for every star)
+                tob = np.asarray(self.t_obs, dtype=np.float64)
+            except ValueError:                    # ragged
+                tob = None
+            if tob is not None and (tob.ndim != 2 or tob.shape[0] != nstars):
+                tob = None
+        if tob is not None:
+            ragged = False
+            nep = np.full(nstars, tob.shape[1], dtype=np.int32)
+        else:
+            rows = [np.ravel(t) for t in self.t_obs]
+            nep = np.fromiter((r.size for r in rows), dtype=np.int32, count=nstars)
+            ragged = True
         if nstars and nep.min() < 1:
             raise ValueError("every star needs at least one observing epoch")
         max_ep = int(nep.max()) if nstars else 1
-        ragged = bool(nstars) and int(nep.min()) != max_ep
-        if nstars and not ragged:
-            tob = np.array(rows, dtype=np.float64)
-        else:
+        if ragged:
             tob = np.zeros((nstars, max_ep), dtype=np.float64)
             for i, r in enumerate(rows):
                 tob[i, :nep[i]] = r
@@ -217,9 +227,19 @@ class BiasCorr(dv.LazyArrays):
                 self.current_star = i
                 e = self.check_error_shape(int(nep[i]))
                 err[i, :nep[i]] = np.ravel(e) if isinstance(e, np.ndarray) else e
-        dev = self._device
-        return (nep, max_ep, dv.to_device(nep, "int32", dev), dv.to_device(tob, "float64", dev),
-                None if err is None else dv.to_device(err, "float32", dev))
+        # one host-to-device copy for the three tables (fp64 first: every view stays aligned)
+        nb = (tob.nbytes, nep.nbytes, 0 if err is None else err.nbytes)
+        packed = np.empty(sum(nb), dtype=np.uint8)
+        packed[:nb[0]] = tob.reshape(-1).view(np.uint8)
+        packed[nb[0]:nb[0] + nb[1]] = nep.view(np.uint8)
+        if err is not None:
+            packed[nb[0] + nb[1]:] = err.reshape(-1).view(np.uint8)
+        t = dv.torch()
+        d = t.from_numpy(packed).to(self._device)
+        d_tobs = d[:nb[0]].view(t.float64).view(nstars, max_ep)
+        d_nep = d[nb[0]:nb[0] + nb[1]].view(t.int32)
+        d_err = None if err is None else d[nb[0] + nb[1]:].view(t.float32).view(nstars, max_ep)
+        return nep, max_ep, d_nep, d_tobs, d_err
 
     def _mass_tables(self):
         dev = self._device
