@@ -339,7 +339,7 @@ def run_gpu_arm(args):
                 "unit": "T lane-instr/s", "frac": rv_per_s_kernel * alg_instr / issue_peak,
                 "peak_source": "%d SMs x 4 schedulers x 32 lanes x %.0f MHz (NVML, sampled during the timed region)"
                                % (sms.value, clk_hz / 1e6),
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "rvmc::biascorr_fused_kernel<6, FAST, QUIRK, !RVOUT>", "launch_ms": launch_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "rvmc::biascorr_fused_kernel<6, FAST, QUIRK, !RVOUT, NOISY>", "launch_ms": launch_ms,
                 "algorithmic_per_unit": {"fp32_flop": ALG_FP32_FLOP, "sfu_ops": ALG_SFU_OPS, "int_ops": ALG_INT_OPS,
                                          "fp64_flop": ALG_FP64_FLOP, "lane_instr": alg_instr, "hbm_bytes": ALG_HBM_BYTES},
                 "ncu": "profiles/r01_biascorr_fused_fullsize_ncu.md (same launch, ncu --set full): 77 % of issue slots "

@@ -84,21 +84,22 @@ __device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint
 }
 
 // NE    : compile-time bound on the epochs per star (<= 16: epoch loop fully unrolled, RVs in registers)
-// FAST  : the headline configuration with every launch-uniform switch resolved at compile time --
-//         measurement errors given, per-epoch RVs written only if RVOUT, one Halley step, fp64 guard proven
-//         unreachable by the host (guard_reachable()), period-law exponent 1 or 2, phase convention
-//         QUIRK.  !FAST keeps all of them as run-time values (same arithmetic, ~15 % more
-//         instructions, and a call to pow() for a general period-law exponent).
-// Each thread walks a.spt samples of its star (1..8, chosen by the host so that the grid still
-// holds >= 8 blocks per SM), so the per-block prologue (epoch tables, pair thresholds, two barriers)
-// is amortised over BC_THREADS * spt binaries.  3 blocks/SM at <= 85 registers measured best.
+// FAST  : every launch-uniform switch resolved at compile time -- phase convention QUIRK, measurement
+//         errors given iff NOISY, per-epoch RVs written iff RVOUT, one Halley step, fp64 guard proven
+//         unreachable by the host (guard_reachable()); a general period-law exponent goes through the
+//         call-free pow_bounded_f64.  These instantiations contain no call and no stack frame.
+//         !FAST keeps the switches as run-time values (same arithmetic, ~15 % more instructions,
+//         run-time Halley count, fp64 guard, pow()).
+// Each thread walks a.spt samples of its star (1..BC_MAX_SPT, chosen by the host so that the grid
+// still holds >= 8 blocks per SM), so the per-block prologue (epoch tables, pair thresholds, two
+// barriers) is amortised over BC_THREADS * spt binaries.  3 blocks/SM at <= 85 registers measured best.
 #ifndef BC_MAX_SPT
 #define BC_MAX_SPT 16
 #endif
 #ifndef BC_MIN_BLOCKS
 #define BC_MIN_BLOCKS 3
 #endif
-template <int NE, bool FAST, bool QUIRK, bool RVOUT>
+template <int NE, bool FAST, bool QUIRK, bool RVOUT, bool NOISY>
 __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kernel(BcArgs a) {
     __shared__ double A_s[NE];            // 2 pi t_obs (quirk) or t_obs (physical)
     __shared__ float err_s[NE];
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
     const int star = a.star0 + (int)blockIdx.y;
     const int ne = a.n_epochs[star];
     RVMC_DEV_ASSERT(star >= 0 && star < a.nstars && ne >= 0 && ne <= NE && ne <= a.max_epochs);
-    const bool noisy = FAST ? true : (a.rv_err != nullptr);
+    const bool noisy = FAST ? NOISY : (a.rv_err != nullptr);
     const bool quirk = FAST ? QUIRK : (a.quirk_phase != 0);
     float* const rv_out = (FAST && !RVOUT) ? nullptr : a.rv_out;
 
@@ -299,13 +300,13 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
     }
 }
 
-template <int NE, bool FAST, bool QUIRK, bool RVOUT>
+template <int NE, bool FAST, bool QUIRK, bool RVOUT, bool NOISY>
 static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
     // gridDim.y carries the star (<= 65535 per launch)
     for (int s0 = 0; s0 < a.nstars; s0 += 65535) {
         a.star0 = s0;
         const int ny = a.nstars - s0 < 65535 ? a.nstars - s0 : 65535;
-        biascorr_fused_kernel<NE, FAST, QUIRK, RVOUT>
+        biascorr_fused_kernel<NE, FAST, QUIRK, RVOUT, NOISY>
             <<<dim3((unsigned int)blocks_per_star, (unsigned int)ny), BC_THREADS, 0, stream>>>(a);
         RVMC_LAUNCH_CHECK();
     }
@@ -315,15 +316,22 @@ static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
 template <int NE>
 static int bc_dispatch(BcArgs& a, bool guard, int64_t blocks_per_star, cudaStream_t stream) {
     if constexpr (NE <= 16) {
-        const bool fast = a.rv_err != nullptr && a.kepler_iters == 1 && !guard;
-        if (fast && a.rv_out)
-            return a.quirk_phase ? bc_launch<NE, true, true, true>(a, blocks_per_star, stream)
-                                 : bc_launch<NE, true, false, true>(a, blocks_per_star, stream);
-        if (fast)
-            return a.quirk_phase ? bc_launch<NE, true, true, false>(a, blocks_per_star, stream)
-                                 : bc_launch<NE, true, false, false>(a, blocks_per_star, stream);
+        // launch-uniform switches -> template arguments (phase convention, RVs written, errors given)
+        if (a.kepler_iters == 1 && !guard) {
+            const int sel = (a.quirk_phase ? 4 : 0) | (a.rv_out ? 2 : 0) | (a.rv_err ? 1 : 0);
+            switch (sel) {
+                case 0: return bc_launch<NE, true, false, false, false>(a, blocks_per_star, stream);
+                case 1: return bc_launch<NE, true, false, false, true>(a, blocks_per_star, stream);
+                case 2: return bc_launch<NE, true, false, true, false>(a, blocks_per_star, stream);
+                case 3: return bc_launch<NE, true, false, true, true>(a, blocks_per_star, stream);
+                case 4: return bc_launch<NE, true, true, false, false>(a, blocks_per_star, stream);
+                case 5: return bc_launch<NE, true, true, false, true>(a, blocks_per_star, stream);
+                case 6: return bc_launch<NE, true, true, true, false>(a, blocks_per_star, stream);
+                default: return bc_launch<NE, true, true, true, true>(a, blocks_per_star, stream);
+            }
+        }
     }
-    return bc_launch<NE, false, false, true>(a, blocks_per_star, stream);
+    return bc_launch<NE, false, false, true, true>(a, blocks_per_star, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

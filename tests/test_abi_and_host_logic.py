@@ -203,7 +203,7 @@ def test_hot_kernels_resource_usage_and_instruction_mix(lib):
             usage[name] = (int(m.group(1)), int(m.group(2)))
     assert "sm_100a" in out
     fast_bc = [k for k in usage if "biascorr_fused_kernelILi6ELb1" in k or "biascorr_fused_kernelILi8ELb1" in k]
-    assert len(fast_bc) == 8          # {6, 8 epochs} x {quirk, physical phase} x {RVs written or not}
+    assert len(fast_bc) == 16         # {6, 8 epochs} x {quirk, physical phase} x {RVs written or not} x {errors or not}
     for k in fast_bc:
         assert usage[k][0] <= 85 and usage[k][1] == 0, (k, usage[k])            # 3 blocks of 256 threads per SM
     single = [k for k in usage if "sigma1d_fused_kernelILb1ELi1ELb0" in k]

@@ -143,6 +143,27 @@ def test_compile_time_instantiation_matches_oracle_within_1e5(variant, quirk):
     assert res["cnt"][0] == ns * sum(len(t) for t in t_obs) and res["cnt"][2] == 0 and res["cnt"][3] == 0
 
 
+@pytest.mark.parametrize("knobs", [dict(kepler_iters=2), dict(guard_amp=2.0), dict(kepler_iters=3, guard_amp=5.0)])
+@pytest.mark.parametrize("noisy", [False, True])
+def test_general_instantiation_halley_count_and_fp64_guard(knobs, noisy):
+    """Configurations the compile-time instantiations do not take -- a run-time Halley count, or an fp64
+    guard the host cannot prove unreachable (threshold lowered so that it engages at ordinary
+    eccentricities) -- run the general instantiation of the same source: same parity bound."""
+    p = _abi.PopParams.defaults(**knobs)
+    nstars, ns, seed = 2, 20000, 31337
+    t_obs = [DAYS6, DAYS6[:4] + 1234.5]
+    res = _fused(p, seed, 5, t_obs, [1e-30, 1e-30] if noisy else None, ns)
+    for i in range(nstars):
+        o = orbits_from_draws(p, seed, biascorr_item(i, np.arange(ns)))
+        want = orc.multi_epoch_rv(t_obs[i], o["time"], o["period"], o["eccentricity"], o["mass_ratio"],
+                                  o["primary_mass"], o["inclination"], o["orbit_rotation"])
+        K = orc.semi_amplitude(o["mass_ratio"], o["primary_mass"], o["period"], o["eccentricity"], o["inclination"])
+        keep = ~near_regime_edge(o, 1e-9)
+        assert g.rel_err(res["rv"][i, :len(t_obs[i])], want, K)[:, keep].max() < 1e-5
+    assert res["cnt"][0] == ns * 10 and res["cnt"][3] == 0
+    assert (res["cnt"][2] > 1000) == ("guard_amp" in knobs)          # guard lanes counted iff it can engage
+
+
 @pytest.mark.parametrize("errors", ["scalar", "per_epoch"])
 def test_fused_noise_and_detection_match_oracle(errors):
     p = _abi.PopParams.defaults()

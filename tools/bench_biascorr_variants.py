@@ -24,14 +24,14 @@ DAYS = np.array([0, 1, 7, 30, 180, 365.0, 400, 500, 730, 800, 900, 1000, 1100, 1
 
 
 def run(name, nstars=100, ns=10 ** 6, ne=6, quirk=1, iters=1, uniform_err=True, mass_mode=0, rv_out=False, steps=10,
-        **pop):
+        no_errors=False, **pop):
     p = _abi.PopParams.defaults(kepler_iters=iters, **pop)
     d_nep = dv.to_device(np.full(nstars, ne, np.int32), "int32", dev)
     d_tobs = dv.to_device(np.tile(DAYS[:ne], (nstars, 1)), "float64", dev)
     err = np.full((nstars, ne), 2.0, np.float32)
     if not uniform_err:
         err = err * np.linspace(0.5, 1.5, ne, dtype=np.float32)[None, :]
-    d_err = dv.to_device(err, "float32", dev)
+    d_err = None if no_errors else dv.to_device(err, "float32", dev)
     masses = dv.to_device(np.full(nstars, 20 * 2e30), "float64", dev) if mass_mode else None
     merr = dv.to_device(np.full(nstars, 2 * 2e30), "float64", dev) if mass_mode == 1 else None
     drv = dv.empty((nstars, ns), "float32", dev)
@@ -57,6 +57,7 @@ def run(name, nstars=100, ns=10 ** 6, ne=6, quirk=1, iters=1, uniform_err=True, 
 
 
 run("headline (quirk phase, 1 Halley step, equal errors)")
+run("no measurement errors (rv_errors=None, the docstring example: Delta-RV only)", no_errors=True)
 run("physical phase", quirk=0)
 run("per-epoch errors (15 pair tests)", uniform_err=False)
 run("two Halley steps (general instantiation)", iters=2)
