@@ -324,11 +324,11 @@ def run_gpu_arm(args):
         # the binding ceiling is the issue rate (1 warp-instruction / clk / SM sub-partition), below the
         # SFU (17 ops) and FP32 (100 flop) ceilings.  peak = SMs x 4 x 32 x SM clock sampled under load.
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at the default size (ncu --set full,
-        # profiles/r01_biascorr_fused_fullsize_ncu.md): 49 KB + 442.40 MB; the algorithmic 500 MB of
+        # profiles/r01_biascorr_fused_fullsize_ncu.md): 1.09 MB + 441.88 MB; the algorithmic 500 MB of
         # results minus what still sits in the 126 MB L2 when the kernel ends
         traffic, traffic_src = args.traffic_bytes, "--traffic-bytes"
         if traffic is None and (nstars, ns) == (100, 10 ** 6):
-            traffic, traffic_src = 442.45e6, "profiles/r01_biascorr_fused_fullsize_ncu.md"
+            traffic, traffic_src = 442.97e6, "profiles/r01_biascorr_fused_fullsize_ncu.md"
         sms = C.c_int()
         _abi.check(lib.rvmc_device_info(local, C.byref(sms), None, None, None))
         clk_hz = 1e6 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
@@ -348,7 +348,7 @@ def run_gpu_arm(args):
                        "evaluated more cheaply than the survey's operation count assumed, so frac (algorithmic work / "
                        "issue ceiling) exceeds the executed issue utilisation; FMA pipe 42 %, ALU 37 %, XU 54 %, "
                        "FP64 6 %, tensor 0 %, DRAM throughput < 2 %",
-                "issue_slots_busy_ncu": 0.771, "executed_lane_instr_per_unit_ncu": 149.7,
+                "issue_slots_busy_ncu": 0.770, "executed_lane_instr_per_unit_ncu": 150.0,
                 "hbm": {"achieved": rv_per_s_kernel * ALG_HBM_BYTES / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "peak_source": "MEASURED_PEAKS.json" if peak_src == "measured" else "fallback 6650 GB/s",
                         "frac": rv_per_s_kernel * ALG_HBM_BYTES / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
