@@ -186,6 +186,39 @@ def test_pmin_vs_age_join_and_fit(tmp_path):
     assert grid.read_best_fit_table(str(tmp_path / "Pmin_ObsSig_10.123_Nstars_12_Mass_6_20.dat"))["best_Pmin"] > 0
 
 
+def test_biascorr_campaign_tables_host_logic():
+    """BiasCorr._tables packs n_epochs / t_obs / rv_err into one upload: regular and ragged campaigns,
+    scalar, per-star and per-epoch errors (check_error_shape, RVMC_bias_corr.py:374-393).  Pure host
+    logic -- exercised on a CPU torch device, no library call involved."""
+    import torch
+    from rvmc_b200.bias_corr import BiasCorr
+
+    def tables(t_obs, rv_errors):
+        bc = object.__new__(BiasCorr)
+        object.__setattr__(bc, "_host", {})
+        object.__setattr__(bc, "_dev", {})
+        object.__setattr__(bc, "_device", torch.device("cpu"))
+        bc.__dict__.update(t_obs=t_obs, number_of_stars=len(t_obs), rv_errors=rv_errors, current_star=0)
+        return bc._tables()
+
+    reg = [np.arange(6.0) * 86400 + i for i in range(5)]
+    nep, max_ep, d_nep, d_tobs, d_err = tables(reg, 2.0)
+    assert max_ep == 6 and nep.tolist() == [6] * 5 and d_nep.dtype == torch.int32 and d_tobs.dtype == torch.float64
+    np.testing.assert_array_equal(d_tobs.numpy(), np.array(reg))
+    np.testing.assert_array_equal(d_err.numpy(), np.full((5, 6), 2.0, np.float32))
+    assert tables(np.array(reg), None)[4] is None                         # a 2-D array works as well
+    rag = [np.array([0.0, 5.0]), np.array([1.0, 2.0, 3.0, 4.0]), [7.0]]
+    nep, max_ep, d_nep, d_tobs, d_err = tables(rag, [1.0, np.array([0.1, 0.2, 0.3, 0.4]), 3.0])
+    assert max_ep == 4 and d_nep.tolist() == [2, 4, 1]
+    np.testing.assert_array_equal(d_tobs.numpy(), [[0, 5, 0, 0], [1, 2, 3, 4], [7, 0, 0, 0]])
+    np.testing.assert_allclose(d_err.numpy(), [[1, 1, 0, 0], [0.1, 0.2, 0.3, 0.4], [3, 0, 0, 0]], rtol=1e-7)
+    np.testing.assert_array_equal(tables(rag, 1.5)[4].numpy(), [[1.5, 1.5, 0, 0], [1.5] * 4, [1.5, 0, 0, 0]])
+    with pytest.raises(ValueError, match="does not match the number of epochs"):
+        tables(rag, [1.0, np.array([0.1, 0.2]), 3.0])
+    with pytest.raises(ValueError, match="at least one observing epoch"):
+        tables([np.array([1.0]), np.array([])], 1.0)
+
+
 def test_hot_kernels_resource_usage_and_instruction_mix(lib):
     """Regression guard from the round-1 tuning: the FAST multi-epoch kernel and the single-population
     fused sigma kernel must stay call-free (no stack frame: a callee such as pow() silently raised the
