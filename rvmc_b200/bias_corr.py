@@ -28,6 +28,9 @@ from .rvmc import _check_powers
 _ORBIT = ("primary_mass", "period", "time", "mass_ratio", "eccentricity", "inclination", "orbit_rotation")
 
 
+_FUSED_MAX_EPOCHS = 64          # rvmc_biascorr_fused: epochs per star (include/rvmc_b200.h)
+
+
 class BiasCorr(dv.LazyArrays):
     """Determines the binary-detection bias of a multi-epoch RV campaign by simulating a population
     of binaries (GPU implementation of RVMC_bias_corr.py:22-476)."""
@@ -451,7 +454,9 @@ class BiasCorr(dv.LazyArrays):
         self._rv_seed = self._next_seed()
         self._rv_user = None
         quirk = 0 if self.physical_phase else 1
-        if self._replay_mode():
+        if self._replay_mode() or max_ep > _FUSED_MAX_EPOCHS:
+            # host-authoritative attributes, or more epochs per star than the fused kernel keeps in
+            # registers: the materialised fp64 path (any number of epochs, RVMC_bias_corr.py:406-422 as written)
             t = self._orbit_on_device()
             pm = t["primary_mass"]
             rv = dv.zeros((nstars, max_ep, ns), "float64", dev)

@@ -343,6 +343,32 @@ def test_biascorr_large_pass_in_star_ranges_equals_one_launch():
     np.testing.assert_array_equal(res[0][2][0], res[0][1].sum(axis=1))
 
 
+@pytest.mark.gpu
+def test_biascorr_more_epochs_than_the_fused_kernel_holds():
+    """A monitoring campaign with more than 64 epochs of one star goes through the materialised fp64
+    path (the reference has no limit): Delta-RV and the detection flags must follow from the class's own
+    attribute arrays by the reference's formulas."""
+    rng = np.random.RandomState(8)
+    t_obs = [np.sort(rng.uniform(0, 3e7, 90)), np.array([0.0, 86400.0, 5e6])]
+    bc = BiasCorr(t_obs, number_of_samples=3000, rv_errors=[1.5, 2.5], seed=21)
+    bc.calculate_radial_velocities()
+    det = bc.get_detected_binaries(delta_RV=20, n_sigma_RV=4)
+    rvs = bc.radial_velocities
+    assert rvs[0].shape == (90, 3000) and rvs[1].shape == (3, 3000) and det.shape == (2, 3000)
+    for i, err in enumerate([1.5, 2.5]):
+        np.testing.assert_allclose(np.asarray(bc.delta_rv)[i], rvs[i].max(axis=0) - rvs[i].min(axis=0), rtol=1e-12)
+        np.testing.assert_array_equal(det[i], orc.detected_binaries(rvs[i], err, 20, 4))
+    clean = BiasCorr(t_obs, number_of_samples=3000, seed=21)
+    clean.calculate_radial_velocities()
+    for i in range(2):
+        want = orc.multi_epoch_rv(t_obs[i], clean.time[i], clean.period[i], clean.eccentricity[i], clean.mass_ratio[i],
+                                  clean.primary_mass[i], clean.inclination[i], clean.orbit_rotation[i])
+        K = orc.semi_amplitude(clean.mass_ratio[i], clean.primary_mass[i], clean.period[i], clean.eccentricity[i],
+                               clean.inclination[i])
+        assert np.max(np.abs(clean.radial_velocities[i] - want) / np.maximum(np.abs(want), K)) < 1e-9
+    assert det[0].mean() > det[1].mean() > 0.05          # 90 epochs catch more binaries than 3
+
+
 def test_biascorr_constructor_errors_and_modes():
     with pytest.raises(ValueError, match="number of masses"):
         BiasCorr([DAYS6, DAYS6], masses=[1e31])
