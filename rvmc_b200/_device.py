@@ -98,10 +98,10 @@ def side_stream(device):
 
 
 def to_host_overlapped(tensor, chunks):
-    """Rows of a [nstars, ...] device tensor -> one pinned NumPy array, copied chunk by chunk on a
-    side stream as soon as the kernel that produced each chunk has finished.  `chunks` is a list of
-    (row0, row1, event) with `event` recorded after that chunk's kernel: the D2H transfer of chunk
-    k overlaps the compute of chunks k+1.. (the copy engine and the SMs work concurrently)."""
+    """Blocks of a [nstars, nsamples] device tensor -> one pinned NumPy array, copied block by block on
+    a side stream as soon as the kernel that produced each block has finished.  `chunks` is a list of
+    (row0, row1, col0, col1, event) with `event` recorded after that block's kernel: the D2H transfer of
+    block k overlaps the compute of blocks k+1.. (the copy engine and the SMs work concurrently)."""
     t = torch()
     dev = tensor.device
     key = (dev.type, dev.index)
@@ -110,9 +110,9 @@ def to_host_overlapped(tensor, chunks):
     cs = _copy_streams[key]
     host = t.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
     with t.cuda.stream(cs):
-        for r0, r1, ev in chunks:
+        for r0, r1, c0, c1, ev in chunks:
             cs.wait_event(ev)
-            host[r0:r1].copy_(tensor[r0:r1], non_blocking=True)
+            host[r0:r1, c0:c1].copy_(tensor[r0:r1, c0:c1], non_blocking=True)
     cs.synchronize()
     return host.numpy()
 

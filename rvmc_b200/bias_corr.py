@@ -476,16 +476,22 @@ class BiasCorr(dv.LazyArrays):
         det = dv.empty((nstars, ns), "uint8", dev) if d_err is not None else None
         counters = dv.zeros((4,), "int64", dev)
         per_star = dv.zeros((max(nstars, 1),), "int32", dev)
-        # large problems go out as a few launches over star ranges: the copy of one range's results
-        # to the host (get_detected_binaries) then overlaps the compute of the next ranges.  The
-        # ranges taper (each about 0.7 of the previous one) so that the last copy, which nothing
-        # overlaps, is small; everything launch-invariant is prepared once.
-        if nstars * ns >= 4_000_000 and nstars > 1:
-            n_chunks = min(nstars, self._d2h_chunks)
+        # large problems go out as a few launches over star ranges (sample ranges when there are only
+        # a few stars): the copy of one range's results to the host (get_detected_binaries) then overlaps
+        # the compute of the next ranges.  The ranges taper (each about 0.7 of the previous one) so that
+        # the last copy, which nothing overlaps, is small; everything launch-invariant is prepared once.
+        ranges = [(0, nstars, 0, ns)]
+        if nstars * ns >= 4_000_000 and self._d2h_chunks > 1:
+            by_star = nstars >= self._d2h_chunks // 2
+            total = nstars if by_star else ns
+            n_chunks = min(total, self._d2h_chunks)
             w = 0.7 ** np.arange(n_chunks)
-            bounds = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * nstars)]).astype(int)
-        else:
-            bounds = np.array([0, nstars])
+            bounds = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * total)]).astype(np.int64)
+            if not by_star:
+                bounds[1:-1] = (bounds[1:-1] + 2047) // 4096 * 4096        # whole blocks of samples
+                bounds = np.unique(np.clip(bounds, 0, ns))
+            ranges = [(int(a), int(b), 0, ns) if by_star else (0, nstars, int(a), int(b))
+                      for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
         chunks = []
         t = dv.torch()
         launch = self._fused_launcher(max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, None, counters,
@@ -493,19 +499,18 @@ class BiasCorr(dv.LazyArrays):
         # the ranges are independent: they alternate between the current stream and a side stream, so the
         # draining tail of one launch is filled by the first blocks of the next
         main = t.cuda.current_stream(dev)
-        streams = [main, dv.side_stream(dev)] if len(bounds) > 2 else [main]
+        streams = [main, dv.side_stream(dev)] if len(ranges) > 1 else [main]
         if len(streams) > 1:
             ready = t.cuda.Event()
             ready.record(main)
             streams[1].wait_event(ready)
         with dv.DeviceGuard(dev):
-            for k, (s0, s1) in enumerate(zip(bounds[:-1], bounds[1:])):
-                if s1 > s0:
-                    st = streams[k % len(streams)]
-                    launch(int(s0), int(s1), C.c_void_p(st.cuda_stream))
-                    ev = t.cuda.Event()
-                    ev.record(st)
-                    chunks.append((int(s0), int(s1), ev))
+            for k, (s0, s1, c0, c1) in enumerate(ranges):
+                st = streams[k % len(streams)]
+                launch(s0, s1, C.c_void_p(st.cuda_stream), c0, c1)
+                ev = t.cuda.Event()
+                ev.record(st)
+                chunks.append((s0, s1, c0, c1, ev))
         if len(streams) > 1:
             done = t.cuda.Event()
             done.record(streams[1])
@@ -517,7 +522,8 @@ class BiasCorr(dv.LazyArrays):
 
     def _fused_launcher(self, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
                         per_star):
-        """-> launch(s0, s1): one rvmc_biascorr_fused call over stars [s0, s1).  Population, mass tables
+        """-> launch(s0, s1, stream, c0, c1): one rvmc_biascorr_fused call over stars [s0, s1) and samples
+        [c0, c1) (default: all).  Population, mass tables
         and base pointers are resolved once; a star range is pointer arithmetic on the row-major
         [nstars, ...] buffers (the caller holds the device guard)."""
         dev = self._device
@@ -539,11 +545,16 @@ class BiasCorr(dv.LazyArrays):
         def rows(b, s0):
             return (b[0] + s0 * b[1]) if b[0] else None
 
-        def launch(s0, s1, stream=stream, _keep=keep):
+        def cols(b, s0, c0, itemsize):
+            return (b[0] + s0 * b[1] + c0 * itemsize) if b[0] else None
+
+        def launch(s0, s1, stream=stream, c0=0, c1=ns, _keep=keep):
+            # the sample index is the Philox counter, so a sample range reproduces the full pass bit for bit
             _abi.check(lib.rvmc_biascorr_fused(
                 C.byref(pop), self._seed0, self._rv_seed, s0, s1 - s0, max_ep, rows(b_nep, s0), rows(b_tobs, s0),
-                rows(b_err, s0), self._mass_mode, rows(b_m, s0), rows(b_me, s0), quirk, args[0], args[1], 0, ns, ns,
-                rows(b_drv, s0), rows(b_det, s0), rows(b_rv, s0), p_cnt, rows(b_star, s0), stream))
+                rows(b_err, s0), self._mass_mode, rows(b_m, s0), rows(b_me, s0), quirk, args[0], args[1], c0, c1 - c0,
+                ns, cols(b_drv, s0, c0, 4), cols(b_det, s0, c0, 1), cols(b_rv, s0, c0, 4), p_cnt, rows(b_star, s0),
+                stream))
         return launch
 
     def _launch_fused(self, nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,

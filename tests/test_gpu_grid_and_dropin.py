@@ -344,6 +344,32 @@ def test_biascorr_large_pass_in_star_ranges_equals_one_launch():
 
 
 @pytest.mark.gpu
+def test_biascorr_few_stars_go_out_in_sample_ranges():
+    """With only a few stars the large pass is split along the sample axis instead (column blocks of
+    the result arrays, Philox counter = sample index): same bits as one launch, ragged epochs included."""
+    days = np.array([0, 1, 7, 30, 180, 365.0]) * 86400.0
+    t_obs = [days, days[:4] + 777.0]
+    res = []
+    saved = BiasCorr._d2h_chunks
+    try:
+        for chunks in (1, 12, 5):
+            BiasCorr._d2h_chunks = chunks
+            bc = BiasCorr(t_obs, number_of_samples=2_300_001, rv_errors=[2.0, np.array([1.0, 2.0, 3.0, 0.5])], seed=5)
+            bc.calculate_radial_velocities()
+            det = bc.get_detected_binaries()
+            res.append((np.asarray(bc.delta_rv).copy(), det.copy(), bc.detection_counts()))
+    finally:
+        BiasCorr._d2h_chunks = saved
+    for drv, det, (per_star, counters) in res[1:]:
+        np.testing.assert_array_equal(drv, res[0][0])
+        np.testing.assert_array_equal(det, res[0][1])
+        np.testing.assert_array_equal(per_star, res[0][2][0])
+        assert counters == res[0][2][1]
+    assert res[0][2][1]["binary_epoch_rvs"] == 2_300_001 * 10
+    np.testing.assert_array_equal(res[0][2][0], res[0][1].sum(axis=1))
+
+
+@pytest.mark.gpu
 def test_biascorr_more_epochs_than_the_fused_kernel_holds():
     """A monitoring campaign with more than 64 epochs of one star goes through the materialised fp64
     path (the reference has no limit): Delta-RV and the detection flags must follow from the class's own

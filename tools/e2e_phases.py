@@ -36,3 +36,18 @@ for chunks in (8, 12, 16, 24):
     acc *= 1e3 / n
     print("chunks %2d: ctor %.3f ms, calculate (launches) %.3f ms, get_detected (wait+D2H) %.3f ms, total %.3f ms -> %.3e RV/s"
           % (chunks, acc[0], acc[1], acc[2], acc[3], nstars * ns * 6 / (acc[3] * 1e-3)))
+
+# a single star with many samples: the pass is split along the sample axis
+for chunks in (1, 12):
+    BiasCorr._d2h_chunks = chunks
+    acc, n = 0.0, 8
+    for k in range(n + 2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bc = BiasCorr([DAYS6], number_of_samples=10 ** 8, rv_errors=2.0, seed=k, device=dev)
+        bc.calculate_radial_velocities()
+        d = bc.get_detected_binaries()
+        torch.cuda.synchronize()
+        if k >= 2:
+            acc += time.perf_counter() - t0
+    print("1 star x 1e8 samples, %2d range(s): %.3f ms -> %.3e RV/s" % (chunks, acc / n * 1e3, 6e8 / (acc / n)))
