@@ -61,7 +61,11 @@ typedef struct rvmc_pop_params {
     double guard_amp;                   /* fp64 guard threshold on the M->nu error amplification
                                            sqrt(1-e^2)/(1-e cos E)^2 (default 64)               */
     int32_t kepler_iters;               /* Halley steps after the closed-form starter (default 1) */
-    int32_t reserved;
+    uint32_t substream;                 /* Philox counter word 3 of every draw of the fused sigma_1D
+                                           kernels (default 0).  Grid points may share a seed and differ
+                                           in substream: statistically independent streams under ONE
+                                           key, which the grid kernels then read as launch-uniform
+                                           operands instead of deriving ten round keys per point    */
 } rvmc_pop_params;
 
 /* SoA view of a materialised population: the public attribute arrays of RVMC.py:80-95.

@@ -23,7 +23,7 @@ class PopParams(C.Structure):
         "min_mass", "max_mass", "mass_power", "min_period", "max_period", "period_pi", "min_q",
         "max_q", "mass_ratio_kappa", "e_power", "e_min", "e_max_mid", "e_max_long", "p_circ_days",
         "p_mid_days", "sigma_dyn", "fbin", "guard_amp")] + [("kepler_iters", C.c_int32),
-                                                             ("reserved", C.c_int32)]
+                                                             ("substream", C.c_uint32)]
 
     @classmethod
     def defaults(cls, **overrides):
@@ -31,7 +31,7 @@ class PopParams(C.Structure):
         p = cls(min_mass=6.0, max_mass=20.0, mass_power=-2.35, min_period=10. ** 0.15,
                 max_period=10. ** 3.5, period_pi=-0.5, min_q=0.1, max_q=1.0, mass_ratio_kappa=0.0,
                 e_power=-0.5, e_min=1e-5, e_max_mid=0.5, e_max_long=0.9, p_circ_days=4.0,
-                p_mid_days=6.0, sigma_dyn=2.0, fbin=0.7, guard_amp=64.0, kepler_iters=1, reserved=0)
+                p_mid_days=6.0, sigma_dyn=2.0, fbin=0.7, guard_amp=64.0, kepler_iters=1, substream=0)
         for k, v in overrides.items():
             if not hasattr(p, k):
                 raise TypeError("unknown population parameter %r" % k)

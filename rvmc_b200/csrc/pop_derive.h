@@ -92,7 +92,7 @@ inline void pop_defaults(rvmc_pop_params* p) {
     p->fbin = 0.7;
     p->guard_amp = 64.0;
     p->kepler_iters = 1;
-    p->reserved = 0;
+    p->substream = 0;
 }
 
 }  // namespace rvmc

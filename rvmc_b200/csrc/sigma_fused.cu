@@ -34,11 +34,13 @@ struct FusedPoint {
     uint32_t seed_lo, seed_hi;
     uint32_t coin_thresh;      // binary iff (word >> 8) < coin_thresh ; coin_thresh = round(fbin * 2^24)
     int32_t kepler_iters;
+    uint32_t sub;              // Philox counter word 3 of this point's draws (rvmc_pop_params.substream)
 };
 
 struct FusedArgs {
     FusedPoint single;         // the population when points == nullptr (single-population launch)
-    PhiloxKey key;             // its expanded key schedule (constant-bank operands of the Philox rounds)
+    PhiloxKey key;             // expanded key schedule (constant-bank operands of the Philox rounds) of the
+                               // single population, or of the seed ALL points of a grid launch share (KEYED)
     const FusedPoint* points;  // device, one per grid point, or nullptr
     const float* meas_err;     // device [S]
     float* sigma_out;          // [n_points][sigma_stride]
@@ -62,9 +64,12 @@ __device__ __forceinline__ float slot_scale(float sigma_dyn, float err) {
 // SINGLE: one population for the whole launch, read straight from the kernel parameters (constant
 //         bank: no staging, no registers spent on it, pre-expanded Philox keys); otherwise one
 //         descriptor per grid point, staged in shared memory.
+// KEYED : every point of the launch has the same seed (the points differ in their substream, i.e. in
+//         the Philox counter): the round keys are the launch-uniform a.key, as for SINGLE, instead of
+//         two integer adds per round and Philox block for a per-point key schedule.
 // ITERS : Halley steps as a compile-time constant (0 = run-time kepler_iters).
 // GUARD : keep the fp64 guard path of the Kepler solve (false when proven unreachable on the host).
-template <bool SINGLE, int ITERS, bool GUARD>
+template <bool SINGLE, bool KEYED, int ITERS, bool GUARD>
 __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S;
@@ -110,8 +115,9 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
     }
 
     const uint64_t seed = seed_of(pt);
+    const uint32_t sub = pt.sub;
     auto draw = [&](uint64_t item, uint32_t stream) {
-        return SINGLE ? philox_block(a.key, item, stream, 0) : philox_block(seed, item, stream, 0);
+        return (SINGLE || KEYED) ? philox_block(a.key, item, stream, sub) : philox_block(seed, item, stream, sub);
     };
     const uint64_t slot0 = (a.first_real + (uint64_t)r0) * (uint64_t)S;
     const uint64_t p_begin = slot0 >> 1;
@@ -211,7 +217,7 @@ struct FbinArgs {
     uint32_t thresh_max;
 };
 
-template <int ITERS, bool GUARD>
+template <bool KEYED, int ITERS, bool GUARD>
 __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FusedArgs& a = fa.base;
@@ -256,6 +262,10 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         wsum_s = s;
     }
     const uint64_t seed = seed_of(pt);
+    const uint32_t sub = pt.sub;
+    auto draw = [&](uint64_t item, uint32_t stream) {
+        return KEYED ? philox_block(a.key, item, stream, sub) : philox_block(seed, item, stream, sub);
+    };
     const uint64_t slot0 = (a.first_real + (uint64_t)r0) * (uint64_t)S;
     const uint64_t p_begin = slot0 >> 1;
     const int npairs = (int)(((slot0 + nslots + 1) >> 1) - p_begin);
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         int l0 = 0, l1 = 0;
         if (pi < npairs) {
             const uint64_t pair = p_begin + pi;
-            const u32x4 w = philox_block(seed, pair, RVMC_STREAM_SLOT, 0);
+            const u32x4 w = draw(pair, RVMC_STREAM_SLOT);
             float z0, z1;
             box_muller_noise_f32(w.z, w.w, z0, z1);
             l0 = (int)(int64_t)(2 * pair - slot0);
@@ -312,8 +322,8 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         const int l = all_binaries ? k : queue[k];
         RVMC_DEV_ASSERT(l >= 0 && l < nslots);
         const uint64_t slot = slot0 + (uint64_t)l;
-        const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, 0);
-        const u32x4 wb = philox_block(seed, slot, RVMC_STREAM_ORBIT_B, 0);
+        const u32x4 wa = draw(slot, RVMC_STREAM_ORBIT_A);
+        const u32x4 wb = draw(slot, RVMC_STREAM_ORBIT_B);
         const OrbitF32 o = sample_orbit_f32(pt.pop, wa, wb);
         int g, b;
         rv[l] = orbit_rv_f32<ITERS, GUARD>(pt.pop, o, pt.kepler_iters, nullptr, g, b);
@@ -389,9 +399,9 @@ __global__ void fused_trace_kernel(FusedPoint pt, const float* __restrict__ meas
     const uint64_t seed = seed_of(pt);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t slot = first_slot + (uint64_t)i;
-        const u32x4 ws = philox_block(seed, slot >> 1, RVMC_STREAM_SLOT, 0);
-        const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, 0);
-        const u32x4 wb = philox_block(seed, slot, RVMC_STREAM_ORBIT_B, 0);
+        const u32x4 ws = philox_block(seed, slot >> 1, RVMC_STREAM_SLOT, pt.sub);
+        const u32x4 wa = philox_block(seed, slot, RVMC_STREAM_ORBIT_A, pt.sub);
+        const u32x4 wb = philox_block(seed, slot, RVMC_STREAM_ORBIT_B, pt.sub);
         float z0, z1;
         box_muller_noise_f32(ws.z, ws.w, z0, z1);
         const int odd = (int)(slot & 1);
@@ -742,7 +752,17 @@ static int make_fused_point(const rvmc_pop_params& p, uint64_t seed, FusedPoint*
     out->seed_hi = (uint32_t)(seed >> 32);
     out->coin_thresh = (uint32_t)llrint(p.fbin * 16777216.0);
     out->kepler_iters = p.kepler_iters;
+    out->sub = p.substream;
     return RVMC_OK;
+}
+
+// The seed every point of a grid call shares (the points then differ in their substream), if any.
+static bool common_seed_of(const std::vector<FusedPoint>& pts, uint64_t* seed) {
+    if (pts.empty()) return false;
+    for (size_t i = 1; i < pts.size(); ++i)
+        if (pts[i].seed_lo != pts[0].seed_lo || pts[i].seed_hi != pts[0].seed_hi) return false;
+    *seed = ((uint64_t)pts[0].seed_hi << 32) | pts[0].seed_lo;
+    return true;
 }
 
 struct TileShape {
@@ -769,7 +789,8 @@ static int fused_tile_shape(int S, TileShape* ts) {
 
 static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, int64_t n_points, const float* meas_err, int S, int weighted,
                         int ddof, uint64_t first_real, int64_t n_real, float* sigma_out, int64_t sigma_stride,
-                        uint64_t* counters, bool iters1, bool guard, cudaStream_t stream) {
+                        uint64_t* counters, bool iters1, bool guard, cudaStream_t stream,
+                        const uint64_t* common_seed = nullptr) {
     TileShape ts;
     int rc = fused_tile_shape(S, &ts);
     if (rc) return rc;
@@ -778,6 +799,7 @@ static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, in
         a.single = *single;
         a.key = philox_key(((uint64_t)single->seed_hi << 32) | single->seed_lo);
     }
+    if (!single && common_seed) a.key = philox_key(*common_seed);      // KEYED: one key for every point
     a.points = d_points;
     a.meas_err = meas_err;
     a.sigma_out = sigma_out;
@@ -807,8 +829,11 @@ static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, in
         return RVMC_OK;
     };
     const bool fast = (single ? single->kepler_iters == 1 : iters1) && !guard;
-    if (single) return fast ? go(sigma1d_fused_kernel<true, 1, false>) : go(sigma1d_fused_kernel<true, 0, true>);
-    return fast ? go(sigma1d_fused_kernel<false, 1, false>) : go(sigma1d_fused_kernel<false, 0, true>);
+    if (single)
+        return fast ? go(sigma1d_fused_kernel<true, true, 1, false>) : go(sigma1d_fused_kernel<true, true, 0, true>);
+    if (common_seed)
+        return fast ? go(sigma1d_fused_kernel<false, true, 1, false>) : go(sigma1d_fused_kernel<false, true, 0, true>);
+    return fast ? go(sigma1d_fused_kernel<false, false, 1, false>) : go(sigma1d_fused_kernel<false, false, 0, true>);
 }
 
 }  // namespace rvmc
@@ -903,6 +928,8 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         iters1 = iters1 && host[i].kepler_iters == 1;
         guard = guard || guard_reachable(points[i].pop);
     }
+    uint64_t shared_seed = 0;
+    const bool keyed = common_seed_of(host, &shared_seed);
     // stream-ordered scratch for the descriptors: no library-global state, so concurrent calls on
     // different streams do not interact
     void* ws = nullptr;
@@ -940,7 +967,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         if (!sigma_out && nb >= 2) rc = cuda_status(cudaStreamWaitEvent(stream, ev_stats[half], 0), "cudaStreamWaitEvent");
         if (rc) break;
         rc = launch_fused(nullptr, d_points + p0, np, meas_err, sample_size, weighted, ddof, 0, n_real, sig, n_real,
-                          counters, iters1, guard, stream);
+                          counters, iters1, guard, stream, keyed ? &shared_seed : nullptr);
         if (rc) break;
         rc = cuda_status(cudaEventRecord(ev_fused, stream), "cudaEventRecord");
         if (!rc) rc = cuda_status(cudaStreamWaitEvent(side, ev_fused, 0), "cudaStreamWaitEvent");
@@ -1013,6 +1040,9 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
         iters1 = iters1 && host[i].kepler_iters == 1;
         guard = guard || guard_reachable(points[i].pop);
     }
+    uint64_t shared_seed = 0;
+    const bool keyed = common_seed_of(host, &shared_seed);
+    if (keyed) fa.base.key = philox_key(shared_seed);
     void* ws = nullptr;
     RVMC_CUDA(cudaMallocAsync(&ws, sizeof(FusedPoint) * (size_t)n_points, stream));
     rc = cuda_status(cudaMemcpyAsync(ws, host.data(), sizeof(FusedPoint) * (size_t)n_points, cudaMemcpyHostToDevice,
@@ -1057,12 +1087,15 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
     if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
     for (int k = 0; k < 2 && !rc; ++k)
         rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
-    if (!rc && smem > 48 * 1024) {
-        rc = cuda_status(cudaFuncSetAttribute(sigma1d_fused_fbins_kernel<1, false>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-        if (!rc) rc = cuda_status(cudaFuncSetAttribute(sigma1d_fused_fbins_kernel<0, true>,
-                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-    }
+    auto launch_fbins = [&](auto kernel, unsigned int total) -> int {
+        if (smem > 48 * 1024) {
+            int rc2 = cuda_status(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                  "smem attr");
+            if (rc2) return rc2;
+        }
+        kernel<<<total, 256, smem, stream>>>(fa);
+        return cuda_status(cudaGetLastError(), "sigma1d_fused_fbins_kernel launch");
+    };
     int64_t nb = 0;
     for (int64_t p0 = 0; p0 < n_points && !rc; p0 += batch, ++nb) {
         const int64_t np = (n_points - p0 < batch) ? n_points - p0 : batch;
@@ -1088,11 +1121,12 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
         fa.base.weighted = weighted;
         fa.base.ddof = ddof;
         const unsigned int total = (unsigned int)(tiles_per_point * np);
-        if (fast)
-            sigma1d_fused_fbins_kernel<1, false><<<total, 256, smem, stream>>>(fa);
+        if (keyed)
+            rc = fast ? launch_fbins(sigma1d_fused_fbins_kernel<true, 1, false>, total)
+                      : launch_fbins(sigma1d_fused_fbins_kernel<true, 0, true>, total);
         else
-            sigma1d_fused_fbins_kernel<0, true><<<total, 256, smem, stream>>>(fa);
-        rc = cuda_status(cudaGetLastError(), "sigma1d_fused_fbins_kernel launch");
+            rc = fast ? launch_fbins(sigma1d_fused_fbins_kernel<false, 1, false>, total)
+                      : launch_fbins(sigma1d_fused_fbins_kernel<false, 0, true>, total);
         if (!rc) rc = cuda_status(cudaEventRecord(ev_fused, stream), "cudaEventRecord");
         if (!rc) rc = cuda_status(cudaStreamWaitEvent(side, ev_fused, 0), "cudaStreamWaitEvent");
         if (rc) break;

@@ -35,7 +35,7 @@ assert STATS_DTYPE.itemsize == C.sizeof(_abi.PointStats) == 80
 # rvmc_grid_point as a NumPy record, so that 10^4-10^5 grid points are built by broadcasting instead
 # of one ctypes object per point
 POINT_DTYPE = np.dtype([(n, "f8") for n, t in _abi.PopParams._fields_ if t is C.c_double] +
-                       [("kepler_iters", "i4"), ("reserved", "i4"), ("seed", "u8")])
+                       [("kepler_iters", "i4"), ("substream", "u4"), ("seed", "u8")])
 assert POINT_DTYPE.itemsize == C.sizeof(_abi.GridPoint)
 POP_FIELDS = tuple(n for n, t in _abi.PopParams._fields_ if t is C.c_double)
 
@@ -126,6 +126,20 @@ def gather_point_stats(local_bytes, n_points, rank, world, group=None):
 # ---------------------------------------------------------------------------------------------
 # core: evaluate a list of grid points
 # ---------------------------------------------------------------------------------------------
+def with_streams(pops, seed, common_random_numbers=False):
+    """The default random streams of a grid: every point under the SAME seed, told apart by its
+    `substream` (the Philox counter word, 0, 1, 2, ... in grid order) -- statistically independent
+    Monte-Carlo runs like successive calls of the reference, while the kernels read one launch-uniform
+    key schedule instead of deriving ten round keys per point.  `common_random_numbers=True` gives every
+    point the same draws (substream 0), which removes most of the point-to-point noise from the statistic
+    surfaces.  Returns `pops` (a POINT_DTYPE record array) with both columns set."""
+    if not (isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE):
+        pops = _as_points(pops, np.zeros(len(pops), dtype=np.uint64))          # a list of PopParams
+    pops["seed"] = np.uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)
+    pops["substream"] = 0 if common_random_numbers else np.arange(len(pops), dtype=np.uint32)
+    return pops
+
+
 def point_seeds(seed, n_points, common_random_numbers=False):
     """Per-point seeds.  Distinct by default (independent Monte-Carlo runs, like successive calls of
     the reference); `common_random_numbers=True` gives every point the same draws, which removes
@@ -366,7 +380,7 @@ def get_Pdistr_stats(measured_errors=np.zeros(12), sample_size=12, pmin=1.4, pma
     periods = np.logspace(np.log10(pmin), np.log10(pmax), Npoints)             # :40
     sd = dv.fresh_seed() if seed is None else seed
     pops = [_pop_for(min_mass, max_mass, fbin, p, max_period, sigma_dyn) for p in periods]
-    res = run_points(pops, point_seeds(sd, len(pops), common_random_numbers), _errs(measured_errors, sample_size),
+    res = run_points(with_streams(pops, sd, common_random_numbers), None, _errs(measured_errors, sample_size),
                      sample_size, number_of_samples, bin=bin, ddof=0, keep_sigma=keep_sigma, keep_hist=True,
                      device=device)
     if verbose:
@@ -384,7 +398,7 @@ def get_fbinDist_stats(measured_errors=np.zeros(12), sample_size=12, fmin=0., fm
     fbins = np.linspace(fmin, fmax, Npoints)                                   # :78
     sd = dv.fresh_seed() if seed is None else seed
     pops = [_pop_for(min_mass, max_mass, f, min_period, max_period, sigma_dyn) for f in fbins]
-    res = run_points(pops, point_seeds(sd, len(pops), common_random_numbers), _errs(measured_errors, sample_size),
+    res = run_points(with_streams(pops, sd, common_random_numbers), None, _errs(measured_errors, sample_size),
                      sample_size, number_of_samples, bin=bin, ddof=0, keep_sigma=keep_sigma, keep_hist=True,
                      device=device)
     if verbose:
@@ -509,13 +523,13 @@ def run_bigGrid(number_stars=20, min_mass=6, max_mass=20, n_fbin=100, n_pmin=100
         # column comes out of one pass over its star slots (rvmc_grid_run_fbins)
         pops = points_array(n_pmin, min_mass=float(min_mass), max_mass=float(max_mass), min_period=periods,
                             max_period=3500.0, sigma_dyn=2.0)
-        res = run_points_fbins(pops, point_seeds(sd, n_pmin, common_random_numbers), fbins, RV_errors, number_stars,
+        res = run_points_fbins(with_streams(pops, sd, common_random_numbers), None, fbins, RV_errors, number_stars,
                                number_of_samples, bin=0.5, ddof=0, keep_hist=single, device=device)
         st = res["stats"].T                                              # [n_fbin, n_pmin]
         hist = None if res["hist"] is None else np.transpose(res["hist"], (1, 0, 2))
     else:
         pops = [_pop_for(min_mass, max_mass, f, p, 3500, 2.0) for f in fbins for p in periods]
-        res = run_points(pops, point_seeds(sd, len(pops), common_random_numbers), RV_errors, number_stars,
+        res = run_points(with_streams(pops, sd, common_random_numbers), None, RV_errors, number_stars,
                          number_of_samples, bin=0.5, ddof=0, keep_hist=single, device=device)
         st = res["stats"].reshape(n_fbin, n_pmin)
         hist = None if res["hist"] is None else res["hist"].reshape(n_fbin, n_pmin, -1)
@@ -567,7 +581,7 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
         cols = dict(base or {})
         cols.update({k: m.ravel() for k, m in zip(names, mesh)})
         pops = points_array(int(np.prod(shape)), **cols)
-        res = run_points(pops, point_seeds(seed, len(pops), common_random_numbers),
+        res = run_points(with_streams(pops, seed, common_random_numbers), None,
                          _errs(measured_errors, sample_size), sample_size, number_of_samples, bin=bin, ddof=ddof,
                          device=device, group=group, distributed=distributed)
         stats = res["stats"].reshape(shape)
@@ -582,7 +596,7 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
             mesh = np.meshgrid(*o_vals, indexing="ij")
             cols.update({k: m.ravel() for k, m in zip(o_names, mesh)})
         pops = points_array(n_other, **cols)
-        res = run_points_fbins(pops, point_seeds(seed, n_other, common_random_numbers), vals[fused_axis],
+        res = run_points_fbins(with_streams(pops, seed, common_random_numbers), None, vals[fused_axis],
                                _errs(measured_errors, sample_size), sample_size, number_of_samples, bin=bin,
                                ddof=ddof, device=device, group=group, distributed=distributed)
         stats = np.moveaxis(res["stats"].reshape(o_shape + (shape[fused_axis],)), -1, fused_axis)

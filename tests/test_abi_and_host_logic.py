@@ -137,6 +137,9 @@ def test_best_fit_rule_and_seeds_and_shards():
         assert grid.best_fit_indices(obs, *curves, usemode=True) == orc.best_fit_indices(obs, *curves, usemode=True)
     far = [500.0] * 4
     assert grid.best_fit_indices(10.0, far, far, far, far, far, far) == (0, 0, 0, 0, 0)    # nothing within 100
+    w = grid.with_streams(grid.points_array(5), 2 ** 64 + 7)
+    assert w["seed"].tolist() == [7] * 5 and w["substream"].tolist() == [0, 1, 2, 3, 4]
+    assert grid.with_streams(grid.points_array(3), 9, True)["substream"].tolist() == [0, 0, 0]
     s = grid.point_seeds(1, 1000)
     assert s.dtype == np.uint64 and len(set(s.tolist())) == 1000 and grid.point_seeds(1, 3, True).tolist() == [1, 1, 1]
     assert np.array_equal(s, grid.point_seeds(1, 1000))
@@ -239,10 +242,10 @@ def test_hot_kernels_resource_usage_and_instruction_mix(lib):
     assert len(fast_bc) == 16         # {6, 8 epochs} x {quirk, physical phase} x {RVs written or not} x {errors or not}
     for k in fast_bc:
         assert usage[k][0] <= 85 and usage[k][1] == 0, (k, usage[k])            # 3 blocks of 256 threads per SM
-    single = [k for k in usage if "sigma1d_fused_kernelILb1ELi1ELb0" in k]
+    single = [k for k in usage if "sigma1d_fused_kernelILb1ELb1ELi1ELb0" in k]
     assert len(single) == 1 and usage[single[0]][0] <= 64 and usage[single[0]][1] == 0, usage[single[0]]
-    multi = [k for k in usage if "sigma1d_fused_kernelILb0ELi1ELb0" in k]
-    assert len(multi) == 1 and usage[multi[0]][0] <= 64
+    multi = [k for k in usage if "sigma1d_fused_kernelILb0ELb0ELi1ELb0" in k or "sigma1d_fused_kernelILb0ELb1ELi1ELb0" in k]
+    assert len(multi) == 2 and all(usage[k][0] <= 64 and usage[k][1] == 0 for k in multi)   # per-point / shared key
     sass = subprocess.run(["cuobjdump", "-sass", _abi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     assert "IMAD.WIDE.U32" in sass and "MUFU.EX2" in sass and "MUFU.LG2" in sass and "DFMA" in sass
     for tensor_op in ("HMMA", "UTCHMMA", "UTCQMMA", "IMMA", "DMMA"):

@@ -115,6 +115,34 @@ def test_fbin_axis_fraction_groups_and_tile_sizes(S, nf, n_real):
         np.testing.assert_array_equal(a["stats"][k].ravel(), b["stats"][k], err_msg=k)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,n_real", [(12, 1500), (40, 257)])
+def test_shared_seed_with_substreams_equals_per_point_keys(S, n_real):
+    """Grid points under one seed, told apart by their substream (the Philox counter word), run kernels
+    that read one launch-uniform key schedule.  Appending a point with a different seed forces the
+    per-point key schedule for the same points: identical bits, in both grid entry points; the
+    single-population entry with the same (seed, substream) agrees too, and substreams differ."""
+    pops = grid.with_streams(grid.points_array(4, period_pi=[-0.5, 0.1, -0.8, -0.5], fbin=[0.7, 0.3, 1.0, 0.7]), 4711)
+    err = np.resize(M17, S)
+    keyed = grid.run_points(pops, None, err, S, n_real, keep_sigma=True, distributed=False)
+    extra = np.concatenate([pops, grid.with_streams(grid.points_array(1), 1234)])
+    unkeyed = grid.run_points(extra, None, err, S, n_real, keep_sigma=True, distributed=False)
+    np.testing.assert_array_equal(keyed["sigma"], unkeyed["sigma"][:4])
+    fb = np.array([0.2, 0.7, 1.0])
+    kf = grid.run_points_fbins(pops, None, fb, err, S, n_real, keep_sigma=True, distributed=False)
+    uf = grid.run_points_fbins(extra, None, fb, err, S, n_real, keep_sigma=True, distributed=False)
+    np.testing.assert_array_equal(kf["sigma"], uf["sigma"][:4])
+    np.testing.assert_array_equal(kf["sigma"][0, 1], keyed["sigma"][0])            # fbin 0.7 of point 0
+    # points 0 and 3 have the same population and seed but different substreams: different draws, same law
+    assert not np.array_equal(keyed["sigma"][0], keyed["sigma"][3])
+    assert abs(np.median(keyed["sigma"][0]) / np.median(keyed["sigma"][3]) - 1) < 0.1
+    one = g.empty((n_real,), "float32")
+    p = _abi.PopParams.defaults(period_pi=0.1, fbin=0.3, substream=1)
+    g.ok(g.lib().rvmc_sigma1d_fused(C.byref(p), 4711, dv.ptr(g.up(err, "float32")), S, 0, 0, 0, n_real, dv.ptr(one),
+                                    None, g.stream()))
+    np.testing.assert_array_equal(g.host(one), keyed["sigma"][1])
+
+
 def test_reference_entry_points_and_best_fit(tmp_path):
     t = grid.get_Pdistr_stats(measured_errors=M17, sample_size=12, pmin=1.4, pmax=3500, Npoints=12, bin=0.5, fbin=0.7,
                               min_mass=6, max_mass=20, number_of_samples=20000, seed=3)
