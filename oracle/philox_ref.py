@@ -57,3 +57,20 @@ def box_muller(w1, w2):
     r = np.sqrt(-2.0 * np.log(u01_open(w1)))
     th = 2 * np.pi * u01(w2)
     return r * np.cos(th), r * np.sin(th)
+
+
+def noise6(w):
+    """rvmc_math.cuh noise6_*: six normals from one Philox block [n, 4] -- three Box-Muller pairs, each
+    from a 22-bit radius uniform in (0, 1] and a 20-bit angle.  Returns [6, n] (z0 = r cos, z1 = r sin)."""
+    w = np.asarray(w, dtype=np.uint64)
+    x, y, z, ww = w[:, 0], w[:, 1], w[:, 2], w[:, 3]
+    u = [x >> 10, y & 0x3FFFFF, (((z << 10) | (ww >> 22)) & 0x3FFFFF)]
+    a = [(((x << 10) | (y >> 22)) & 0xFFFFF), z >> 12, (ww >> 2) & 0xFFFFF]
+    out = np.empty((6, len(w)))
+    for p in range(3):
+        r = np.sqrt(-2.0 * np.log((u[p].astype(np.float64) + 1.0) * 2.0 ** -22))
+        th = a[p].astype(np.float64) * 5.9921124526782858e-06
+        out[2 * p] = r * np.cos(th)
+        out[2 * p + 1] = r * np.sin(th)
+    return out
+

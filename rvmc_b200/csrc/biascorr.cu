@@ -16,7 +16,7 @@
 // memory.  Per binary: two Philox blocks -> orbit; the period and the per-epoch phase reduction
 // run in fp64 (2 pi t / P reaches ~2e3 turns: fp32 would lose the phase), everything after the
 // mean anomaly is fp32: closed-form starter + Halley, closed-form true anomaly, RV.  Noise is
-// one Philox block per four epochs.  max/min and the pairwise test are taken in registers; only
+// one Philox block per six epochs.  max/min and the pairwise test are taken in registers; only
 // Delta-RV (4 B) and the detection flag (1 B) per binary reach HBM, and both are optional.
 #include "common.cuh"
 #include "pop_derive.h"
@@ -71,16 +71,12 @@ __device__ __forceinline__ double bc_mass_f64(const PopF64& P, int mode, const d
     return masses[star] + mass_errors[star] * ((item & 1) ? z1 : z0);
 }
 
-// Noise normals of epochs 4g..4g+3 of one binary.
-__device__ __forceinline__ void bc_noise4_f32(const PhiloxKey& K, uint64_t item, uint32_t stream, int g, float z[4]) {
-    const u32x4 w = philox_block(K, item, stream, (uint32_t)g);
-    box_muller_noise_f32(w.x, w.y, z[0], z[1]);
-    box_muller_noise_f32(w.z, w.w, z[2], z[3]);
+// Noise normals of epochs 6g..6g+5 of one binary: one Philox block (noise6_*, rvmc_math.cuh).
+__device__ __forceinline__ void bc_noise6_f32(const PhiloxKey& K, uint64_t item, uint32_t stream, int g, float z[6]) {
+    noise6_f32(philox_block(K, item, stream, (uint32_t)g), z);
 }
-__device__ __forceinline__ void bc_noise4_f64(uint64_t seed, uint64_t item, uint32_t stream, int g, double z[4]) {
-    const u32x4 w = philox_block(seed, item, stream, (uint32_t)g);
-    box_muller_f64(w.x, w.y, z[0], z[1]);
-    box_muller_f64(w.z, w.w, z[2], z[3]);
+__device__ __forceinline__ void bc_noise6_f64(uint64_t seed, uint64_t item, uint32_t stream, int g, double z[6]) {
+    noise6_f64(philox_block(seed, item, stream, (uint32_t)g), z);
 }
 
 // NE    : compile-time bound on the epochs per star (<= 16: epoch loop fully unrolled, RVs in registers)
@@ -208,9 +204,9 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
         // ---- epochs -----------------------------------------------------------------------------
         float rvs[NE];
         float vmax = -INFINITY, vmin = INFINITY;
-        float z[4];
+        float z[6];
         auto epoch = [&](int k) {
-            if (noisy && (k & 3) == 0) bc_noise4_f32(a.noise_key, item, RVMC_STREAM_EPOCH, k >> 2, z);
+            if (noisy && (k % 6) == 0) bc_noise6_f32(a.noise_key, item, RVMC_STREAM_EPOCH, k / 6, z);
             float M;
             double M64;
             bool neg = false;
@@ -232,7 +228,7 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
                                                       a.P32.guard_amp, g, b);
             my_guard += g;
             my_bad += b;
-            if (noisy) rv = fmaf(err_s[k], z[k & 3], rv);
+            if (noisy) rv = fmaf(err_s[k], z[k % 6], rv);
             rvs[k] = rv;
             vmax = fmaxf(vmax, rv);
             vmin = fminf(vmin, rv);
@@ -385,15 +381,15 @@ __global__ void biascorr_replay_f64_kernel(int nstars, int64_t n_samples, int ma
         const uint64_t item = bc_item(star, first_sample + (uint64_t)i);
         double vmax = -INFINITY, vmin = INFINITY;
         bool any_nan = false;
-        double z[4];
+        double z[6];
         for (int k = 0; k < ne; ++k) {
-            if (rv_err && (k & 3) == 0) bc_noise4_f64(seed, item, RVMC_STREAM_EPOCH, k >> 2, z);
+            if (rv_err && (k % 6) == 0) bc_noise6_f64(seed, item, RVMC_STREAM_EPOCH, k / 6, z);
             const double tt = t_obs[(size_t)star * max_epochs + k] + time;
             const double M = mean_anomaly_epoch_f64(tt, P, quirk);
             double resid;
             const double E = kepler_f64(M, e, resid);
             double rv = rv_from_K_f64(K, e, w, E);
-            if (rv_err) rv += (double)rv_err[(size_t)star * max_epochs + k] * z[k & 3];
+            if (rv_err) rv += (double)rv_err[(size_t)star * max_epochs + k] * z[k % 6];
             if (rv_out) rv_out[((size_t)star * max_epochs + k) * n_samples + i] = rv;
             any_nan |= (rv != rv);
             vmax = fmax(vmax, rv);
@@ -445,10 +441,10 @@ __global__ void biascorr_singles_kernel(uint64_t seed, int nstars, int max_epoch
         const uint64_t item = bc_item(star, first_single + (uint64_t)i);
         const int ne = n_epochs[star];
         double vmax = -INFINITY, vmin = INFINITY;
-        double z[4];
+        double z[6];
         for (int k = 0; k < ne; ++k) {
-            if ((k & 3) == 0) bc_noise4_f64(seed, item, RVMC_STREAM_SINGLE, k >> 2, z);
-            const double rv = (double)rv_err[(size_t)star * max_epochs + k] * z[k & 3];
+            if ((k % 6) == 0) bc_noise6_f64(seed, item, RVMC_STREAM_SINGLE, k / 6, z);
+            const double rv = (double)rv_err[(size_t)star * max_epochs + k] * z[k % 6];
             vmax = fmax(vmax, rv);
             vmin = fmin(vmin, rv);
         }

@@ -14,6 +14,14 @@
 #define RVMC_HD inline
 #endif
 
+// Rounds of the generator.  10 is the Random123 default (Philox4x32-10) and what every result, test
+// vector and figure of this repository uses; Salmon et al. (SC'11) report 7 as the smallest count that
+// passes BigCrush.  A build with -DRVMC_PHILOX_ROUNDS=7 exists for experiments only (the known-answer
+// tests then fail by design).
+#ifndef RVMC_PHILOX_ROUNDS
+#define RVMC_PHILOX_ROUNDS 10
+#endif
+
 namespace rvmc {
 
 struct u32x4 {
@@ -75,7 +83,7 @@ RVMC_HD u32x4 philox_block(const PhiloxKey& K, uint64_t item, uint32_t stream, u
     c.z = stream;
     c.w = sub;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < RVMC_PHILOX_ROUNDS; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo32(M0, c.x, hi0, lo0);
         mulhilo32(M1, c.z, hi1, lo1);
@@ -96,7 +104,7 @@ RVMC_HD u32x4 philox_block(uint64_t seed, uint64_t item, uint32_t stream, uint32
     c.y = (uint32_t)(item >> 32);
     c.z = stream;
     c.w = sub;
-    return philox4x32<10>(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox4x32<RVMC_PHILOX_ROUNDS>(c, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
 // 24-bit uniforms.  Both precisions consume the SAME value u = (w >> 8) * 2^-24 (exact in fp32),

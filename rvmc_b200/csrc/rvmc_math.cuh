@@ -266,6 +266,51 @@ RVMC_HD void box_muller_noise_f32(uint32_t w1, uint32_t w2, float& z0, float& z1
     box_muller_f32(w1, w2, z0, z1);
 #endif
 }
+// Six normals from ONE Philox block: three Box-Muller pairs, each from a 22-bit radius uniform in
+// (0, 1] (largest deviate 5.5 sigma against 5.8 for 24 bits) and a 20-bit angle (6e-6 rad): 126 of the
+// block's 128 bits.  The measurement noise of the multi-epoch path draws from it -- six epochs per
+// block instead of four -- which takes a whole Philox block (20 IMAD.WIDE, ~65 instructions) off every
+// binary of a six-epoch campaign.  u[], a[]: the integer fields, shared by both precisions.
+RVMC_HD void noise6_fields(const u32x4& w, uint32_t u[3], uint32_t a[3]) {
+    u[0] = w.x >> 10;
+    a[0] = ((w.x << 10) | (w.y >> 22)) & 0xfffffu;
+    u[1] = w.y & 0x3fffffu;
+    a[1] = w.z >> 12;
+    u[2] = ((w.z << 10) | (w.w >> 22)) & 0x3fffffu;
+    a[2] = (w.w >> 2) & 0xfffffu;
+}
+RVMC_HD void noise6_f32(const u32x4& w, float z[6]) {
+    uint32_t u[3], a[3];
+    noise6_fields(w, u, a);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int p = 0; p < 3; ++p) {
+        const float u1 = (float)(u[p] + 1u) * 2.384185791015625e-07f;                   // 2^-22
+        const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));                 // sqrt(-2 ln u1)
+        const float th = (float)a[p] * 5.9921124526782858e-06f;                         // 2 pi 2^-20
+        float s, c;
+#if defined(__CUDA_ARCH__)
+        asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+        asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
+#else
+        s = sinf(th);
+        c = cosf(th);
+#endif
+        z[2 * p] = r * c;
+        z[2 * p + 1] = r * s;
+    }
+}
+RVMC_HD void noise6_f64(const u32x4& w, double z[6]) {
+    uint32_t u[3], a[3];
+    noise6_fields(w, u, a);
+    for (int p = 0; p < 3; ++p) {
+        const double r = sqrt(-2.0 * log((double)(u[p] + 1u) * 2.384185791015625e-07));
+        const double th = (double)a[p] * 5.9921124526782858e-06;
+        z[2 * p] = r * cos(th);
+        z[2 * p + 1] = r * sin(th);
+    }
+}
 RVMC_HD void box_muller_f64(uint32_t w1, uint32_t w2, double& z0, double& z1) {
     const double u1 = u01_open_f64(w1);
     const double r = sqrt(-2.0 * log(u1));

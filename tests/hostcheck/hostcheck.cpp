@@ -106,6 +106,19 @@ void hc_box_muller(int64_t n, const uint32_t* w1, const uint32_t* w2, float* z0,
     }
 }
 
+// six normals per Philox block: w is [n][4] words, z32 / z64 are [n][6]
+void hc_noise6(int64_t n, const uint32_t* w, float* z32, double* z64) {
+    for (int64_t i = 0; i < n; ++i) {
+        u32x4 b;
+        b.x = w[4 * i];
+        b.y = w[4 * i + 1];
+        b.z = w[4 * i + 2];
+        b.w = w[4 * i + 3];
+        noise6_f32(b, z32 + 6 * i);
+        noise6_f64(b, z64 + 6 * i);
+    }
+}
+
 void hc_exp10_fast(int64_t n, const double* y, double* out) {
     for (int64_t i = 0; i < n; ++i) out[i] = exp10_fast_f64(y[i]);
 }

@@ -84,14 +84,12 @@ def biascorr_item(star, sample):
 
 
 def biascorr_noise_from_draws(noise_seed, star, samples, n_epochs, err, stream=None):
-    """(n_epochs, n_samples) measurement errors: one STREAM_EPOCH block per four epochs."""
+    """(n_epochs, n_samples) measurement errors: one STREAM_EPOCH block per six epochs (noise6)."""
     stream = ph.STREAM_EPOCH if stream is None else stream
     items = biascorr_item(star, samples)
     out = np.zeros((n_epochs, len(items)))
-    for g in range((n_epochs + 3) // 4):
-        w = ph.philox_block(noise_seed, items, stream, g)
-        za, zb = ph.box_muller(w[:, 0], w[:, 1])
-        zc, zd = ph.box_muller(w[:, 2], w[:, 3])
-        for k, z in zip(range(4 * g, min(4 * g + 4, n_epochs)), (za, zb, zc, zd)):
-            out[k] = z * np.asarray(err, dtype=np.float64).reshape(-1)[k if np.size(err) > 1 else 0]
+    for g in range((n_epochs + 5) // 6):
+        z6 = ph.noise6(ph.philox_block(noise_seed, items, stream, g))
+        for k in range(6 * g, min(6 * g + 6, n_epochs)):
+            out[k] = z6[k - 6 * g] * np.asarray(err, dtype=np.float64).reshape(-1)[k if np.size(err) > 1 else 0]
     return out

@@ -189,6 +189,30 @@ def test_box_muller_and_sincos():
     assert s[E == 0][0] == 0.0 and c[E == 0][0] == 1.0
 
 
+def test_noise6_six_normals_per_block():
+    """noise6_*: the device source (compiled for the host) against the NumPy model of the bit fields,
+    plus the distribution the fields are meant to give."""
+    lib = load_hostcheck()
+    rng = np.random.RandomState(3)
+    n = 200000
+    w = rng.randint(0, 2 ** 32, (n, 4), dtype=np.uint64).astype(np.uint32)
+    w[0] = 0                                   # smallest radius uniform, angle 0
+    w[1] = 0xFFFFFFFF                          # u1 = 1 exactly -> r = 0
+    z32, z64 = np.empty((n, 6), np.float32), np.empty((n, 6))
+    lib.hc_noise6(C.c_int64(n), w.ctypes.data_as(C.c_void_p), z32.ctypes.data_as(C.c_void_p),
+                  z64.ctypes.data_as(C.c_void_p))
+    want = ph.noise6(w).T
+    assert np.max(np.abs(z64 - want)) < 1e-12
+    assert np.max(np.abs(z32 - want)) < 5e-6
+    assert abs(want[0, 0] - np.sqrt(-2 * np.log(2.0 ** -22))) < 1e-12 and np.all(want[1] == 0)
+    assert np.abs(want).max() <= 5.5226 and abs(want.mean()) < 5e-3 and abs(want.std() - 1) < 5e-3
+    # the six normals of a block are uncorrelated (disjoint bit fields)
+    c = np.corrcoef(want[2:].T)
+    assert np.max(np.abs(c - np.eye(6))) < 0.01
+    from scipy import stats as sps
+    assert sps.kstest(want[2:, 3], "norm").pvalue > 1e-3
+
+
 def test_exp10_fast_f64():
     lib = load_hostcheck()
     y = np.concatenate([np.linspace(-12, 6, 200001), [0.0, -4.9365137424788932 - 0.15, -4.9365137424788932 - 3.5]])
