@@ -324,11 +324,11 @@ def run_gpu_arm(args):
         # the binding ceiling is the issue rate (1 warp-instruction / clk / SM sub-partition), below the
         # SFU (17 ops) and FP32 (100 flop) ceilings.  peak = SMs x 4 x 32 x SM clock sampled under load.
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at the default size (ncu --set full,
-        # profiles/r01_biascorr_fused_fullsize_ncu.md): 1.09 MB + 441.88 MB; the algorithmic 500 MB of
+        # profiles/r01_biascorr_fused_fullsize_ncu.md): 0.13 MB + 442.49 MB; the algorithmic 500 MB of
         # results minus what still sits in the 126 MB L2 when the kernel ends
         traffic, traffic_src = args.traffic_bytes, "--traffic-bytes"
         if traffic is None and (nstars, ns) == (100, 10 ** 6):
-            traffic, traffic_src = 442.97e6, "profiles/r01_biascorr_fused_fullsize_ncu.md"
+            traffic, traffic_src = 442.62e6, "profiles/r01_biascorr_fused_fullsize_ncu.md"
         sms = C.c_int()
         _abi.check(lib.rvmc_device_info(local, C.byref(sms), None, None, None))
         clk_hz = 1e6 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
@@ -343,12 +343,12 @@ def run_gpu_arm(args):
                 "algorithmic_per_unit": {"fp32_flop": ALG_FP32_FLOP, "sfu_ops": ALG_SFU_OPS, "int_ops": ALG_INT_OPS,
                                          "fp64_flop": ALG_FP64_FLOP, "lane_instr": alg_instr, "hbm_bytes": ALG_HBM_BYTES},
                 "ncu": "profiles/r01_biascorr_fused_fullsize_ncu.md (same launch, ncu --set full): 77 % of issue slots "
-                       "busy; 150 EXECUTED thread-instructions per unit -- fewer than the 178 algorithmic ones of SURVEY "
+                       "busy; 142 EXECUTED thread-instructions per unit -- fewer than the 178 algorithmic ones of SURVEY "
                        "8d, because sin/cos of the eccentric anomaly, the cubic starter and the noise normals are "
                        "evaluated more cheaply than the survey's operation count assumed, so frac (algorithmic work / "
-                       "issue ceiling) exceeds the executed issue utilisation; FMA pipe 42 %, ALU 37 %, XU 54 %, "
-                       "FP64 6 %, tensor 0 %, DRAM throughput < 2 %",
-                "issue_slots_busy_ncu": 0.770, "executed_lane_instr_per_unit_ncu": 150.0,
+                       "issue ceiling) exceeds the executed issue utilisation; FMA pipe 43 %, ALU 36 %, XU 54 %, "
+                       "FP64 7 %, tensor 0 %, DRAM throughput < 2 %",
+                "issue_slots_busy_ncu": 0.776, "executed_lane_instr_per_unit_ncu": 142.4,
                 "hbm": {"achieved": rv_per_s_kernel * ALG_HBM_BYTES / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "peak_source": "MEASURED_PEAKS.json" if peak_src == "measured" else "fallback 6650 GB/s",
                         "frac": rv_per_s_kernel * ALG_HBM_BYTES / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
