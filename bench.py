@@ -214,13 +214,19 @@ def run_gpu_arm(args):
     d_tobs = dv.to_device(np.tile(DAYS6, (nstars, 1)), "float64", dev)
     d_err = dv.to_device(np.full((nstars, 6), 2.0, np.float32), "float32", dev)
     drv = dv.empty((nstars, ns), "float32", dev)
-    det = dv.empty((nstars, ns), "uint8", dev)
+    # the outputs of the product path (BiasCorr.calculate_radial_velocities): Delta-RV per binary and the
+    # detection flags, bit-packed (or one byte each with --flag-transfer bytes)
+    nw = (ns + 31) // 32
+    det = dv.empty((nstars, ns), "uint8", dev) if args.flag_transfer == "bytes" else None
+    bits = dv.empty((nstars, nw), "int32", dev) if args.flag_transfer == "bits" else None
     cnt = dv.zeros((4,), "int64", dev)
+    BiasCorr.flag_transfer = args.flag_transfer
 
     def step():
-        _abi.check(lib.rvmc_biascorr_fused(C.byref(p), seed, noise_seed, 0, nstars, 6, dv.ptr(d_nep), dv.ptr(d_tobs),
-                                           dv.ptr(d_err), 0, None, None, 1, 20.0, 4.0, first_sample, ns, ns,
-                                           dv.ptr(drv), dv.ptr(det), None, dv.ptr(cnt), None, st))
+        _abi.check(lib.rvmc_biascorr_fused_packed(C.byref(p), seed, noise_seed, 0, nstars, 6, dv.ptr(d_nep),
+                                                  dv.ptr(d_tobs), dv.ptr(d_err), 0, None, None, 1, 20.0, 4.0,
+                                                  first_sample, ns, ns, dv.ptr(drv), dv.ptr(det), dv.ptr(bits), nw,
+                                                  None, dv.ptr(cnt), None, st))
 
     def barrier():
         torch.cuda.synchronize()
@@ -257,7 +263,7 @@ def run_gpu_arm(args):
     # ---- e2e: the drop-in class with host inputs and the detection array back on the host ----------
     t_obs_host = [DAYS6.copy() for _ in range(nstars)]
     h2d = nstars * 6 * 8 + nstars * 6 * 4 + nstars * 4
-    d2h = nstars * ns
+    d2h = nstars * ns if args.flag_transfer == "bytes" else nstars * nw * 4
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step(k):
@@ -401,6 +407,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--stars", type=int, default=100)
     ap.add_argument("--samples", type=int, default=10 ** 6)
+    ap.add_argument("--flag-transfer", default=os.environ.get("RVMC_FLAG_TRANSFER", "bits"), choices=["bits", "bytes"],
+                    help="how the detection flags reach the host: bit-packed + host unpack (default) or uint8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipe-peaks", action="store_true")
     ap.add_argument("--no-grid", action="store_true", help="skip the secondary grid-points/s measurement")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RVMC_ABI_VERSION 1
+#define RVMC_ABI_VERSION 2
 
 /* the library is built with -fvisibility=hidden: only the entry points below are exported */
 #if defined(__GNUC__)
@@ -226,6 +226,33 @@ RVMC_API int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64
                         uint64_t first_sample, int64_t n_samples, int64_t sample_stride,
                         float* delta_rv, uint8_t* detected, float* rv_out, uint64_t* counters,
                         uint32_t* det_per_star, void* cuda_stream);
+
+/* rvmc_biascorr_fused with the detection flags BIT-PACKED: detected_bits uint32[nstars*bits_stride],
+ * bit j of word w of a star's row = sample 32 w + j of this call (np.unpackbits bitorder="little" on a
+ * little-endian host); one __ballot_sync per warp, 1/8 of the bytes of `detected`.  The `bool
+ * (n_stars, n_samples)` array of RVMC_bias_corr.py:451-476 is 1 bit of information per binary: this
+ * is the form it should cross PCIe in (rvmc_unpack_bits_host widens it on the host).  A caller that
+ * shards the samples passes the word holding ITS first sample, so `first` columns of a shard must be
+ * multiples of 32.  bits_stride >= ceil(n_samples / 32) words.  Either flag output may be NULL. */
+RVMC_API int rvmc_biascorr_fused_packed(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int first_star,
+                               int nstars, int max_epochs,
+                               const int32_t* n_epochs, const double* t_obs, const float* rv_err,
+                               int mass_mode, const double* masses, const double* mass_errors,
+                               int quirk_phase, float delta_rv_min, float n_sigma,
+                               uint64_t first_sample, int64_t n_samples, int64_t sample_stride,
+                               float* delta_rv, uint8_t* detected, uint32_t* detected_bits, int64_t bits_stride,
+                               float* rv_out, uint64_t* counters, uint32_t* det_per_star, void* cuda_stream);
+
+/* HOST helpers for the packed flags (no GPU work; every pointer is a HOST pointer).
+ * rvmc_unpack_bits_host: out_host[r*out_stride + c] = bit c of row r (0/1 bytes == NumPy bool) for
+ *   r < n_rows, c < n_cols, with up to n_threads threads of a persistent pool (the calling thread is
+ *   one of them).  bits_host / out_host may point INTO larger arrays (sub-blocks of a sharded pass).
+ * rvmc_count_bits_host: counts_host[r] = number of set flags of row r (detection counts per star
+ *   without ever widening the flags). */
+RVMC_API int rvmc_unpack_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, int64_t n_rows,
+                          int64_t n_cols, uint8_t* out_host, int64_t out_stride, int n_threads);
+RVMC_API int rvmc_count_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, int64_t n_rows,
+                         int64_t n_cols, int64_t* counts_host, int n_threads);
 
 /* Materialised per-binary attribute arrays of BiasCorr (RVMC_bias_corr.py:175-243) for the
  * same (seed, star, sample) indexing as rvmc_biascorr_fused; fp64, layout [nstars][n_samples]. */

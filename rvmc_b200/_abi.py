@@ -96,6 +96,10 @@ SIGNATURES = {
     "rvmc_fused_trace": (_I, [C.POINTER(PopParams), _U64, _VP, _I, _U64, _I64, TraceSoA, _VP]),
     "rvmc_biascorr_fused": (_I, [C.POINTER(PopParams), _U64, _U64, _I, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _I, _F,
                                  _F, _U64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rvmc_biascorr_fused_packed": (_I, [C.POINTER(PopParams), _U64, _U64, _I, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _I,
+                                        _F, _F, _U64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),
+    "rvmc_unpack_bits_host": (_I, [_VP, _I64, _I64, _I64, _VP, _I64, _I]),
+    "rvmc_count_bits_host": (_I, [_VP, _I64, _I64, _I64, _VP, _I]),
     "rvmc_biascorr_sample": (_I, [C.POINTER(PopParams), _U64, _I, _I, _VP, _VP, _U64, _I64, _U32, OrbitSoA, _VP]),
     "rvmc_kepler_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "rvmc_rv_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
@@ -126,7 +130,7 @@ def lib():
         fn = getattr(l, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if l.rvmc_abi_version() != 1:
+    if l.rvmc_abi_version() != 2:
         raise RuntimeError("rvmc_b200: ABI version mismatch")
     _lib = l
     return l

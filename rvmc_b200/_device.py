@@ -68,19 +68,54 @@ def to_device(array, dtype, device):
     return t.from_numpy(a).to(device)
 
 
+# Pinned host memory comes from torch's caching host allocator, which rounds sizes up to a power of two
+# and never returns blocks to the OS.  Results up to PIN_DIRECT_MAX land in a pinned block directly (the
+# NumPy array keeps it alive; it goes back to the cache when the array is collected).  Anything larger
+# is staged through two fixed pinned buffers into ordinary pageable memory, so reading a multi-GB
+# attribute array cannot grow the locked memory of the process.
+PIN_DIRECT_MAX = 256 << 20
+PIN_STAGE_BYTES = 32 << 20
+_stage = {}
+
+
+def _stage_buffers(device):
+    t = torch()
+    key = (device.type, device.index)
+    if key not in _stage:
+        _stage[key] = ([t.empty(PIN_STAGE_BYTES, dtype=t.uint8, pin_memory=True) for _ in range(2)],
+                       [t.cuda.Event(), t.cuda.Event()])
+    return _stage[key]
+
+
 def to_host(tensor):
-    """Device tensor -> NumPy array.  Large copies land in pinned host memory from torch's caching
-    host allocator (fast DMA, no per-call page pinning after the first use); the array keeps the
-    pinned block alive and returns it to the cache when it is garbage collected."""
+    """Device tensor -> NumPy array (see PIN_DIRECT_MAX above for where the bytes land)."""
     t = torch()
     tensor = tensor.detach()
-    if tensor.is_cuda and tensor.numel() * tensor.element_size() >= (1 << 20):
-        tensor = tensor.contiguous()
+    nbytes = tensor.numel() * tensor.element_size()
+    if not tensor.is_cuda or nbytes < (1 << 20):
+        return tensor.cpu().numpy()
+    tensor = tensor.contiguous()
+    stream = t.cuda.current_stream(tensor.device)
+    if nbytes <= PIN_DIRECT_MAX:
         host = t.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
         host.copy_(tensor, non_blocking=True)
-        t.cuda.current_stream(tensor.device).synchronize()
+        stream.synchronize()
         return host.numpy()
-    return tensor.cpu().numpy()
+    out = t.empty(tensor.shape, dtype=tensor.dtype)          # pageable
+    src = tensor.view(-1).view(t.uint8)
+    dst = out.view(-1).view(t.uint8)
+    bufs, evs = _stage_buffers(tensor.device)
+    n_chunks = (nbytes + PIN_STAGE_BYTES - 1) // PIN_STAGE_BYTES
+    for k in range(n_chunks + 1):
+        if k < n_chunks:                                     # start the copy of chunk k ...
+            lo, hi = k * PIN_STAGE_BYTES, min(nbytes, (k + 1) * PIN_STAGE_BYTES)
+            bufs[k & 1][:hi - lo].copy_(src[lo:hi], non_blocking=True)
+            evs[k & 1].record(stream)
+        if k >= 1:                                           # ... while chunk k-1 moves to its final place
+            lo, hi = (k - 1) * PIN_STAGE_BYTES, min(nbytes, k * PIN_STAGE_BYTES)
+            evs[(k - 1) & 1].synchronize()
+            dst[lo:hi].copy_(bufs[(k - 1) & 1][:hi - lo])
+    return out.numpy()
 
 
 _copy_streams = {}
@@ -97,24 +132,97 @@ def side_stream(device):
     return _side_streams[key]
 
 
-def to_host_overlapped(tensor, chunks):
-    """Blocks of a [nstars, nsamples] device tensor -> one pinned NumPy array, copied block by block on
-    a side stream as soon as the kernel that produced each block has finished.  `chunks` is a list of
-    (row0, row1, col0, col1, event) with `event` recorded after that block's kernel: the D2H transfer of
-    block k overlaps the compute of blocks k+1.. (the copy engine and the SMs work concurrently)."""
+def _copy_stream(dev):
     t = torch()
-    dev = tensor.device
     key = (dev.type, dev.index)
     if key not in _copy_streams:
         _copy_streams[key] = t.cuda.Stream(device=dev)
-    cs = _copy_streams[key]
-    host = t.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
+    return _copy_streams[key]
+
+
+def _host_result(shape, dtype):
+    """Host tensor for a result the caller keeps: pinned (cached by torch) up to PIN_DIRECT_MAX."""
+    t = torch()
+    nbytes = t.empty(0, dtype=dtype).element_size()
+    for d in shape:
+        nbytes *= int(d)
+    return t.empty(shape, dtype=dtype, pin_memory=nbytes <= PIN_DIRECT_MAX)
+
+
+def _copy_block(dst, src, r0, r1, c0, c1):
+    """Asynchronous copy of the block [r0:r1, c0:c1]: whole rows go as one contiguous transfer, a column
+    range goes row by row (each slice contiguous -- a strided 2-D slice would make torch stage the copy
+    through pageable memory and lose the overlap)."""
+    if c0 == 0 and c1 == src.shape[1]:
+        dst[r0:r1].copy_(src[r0:r1], non_blocking=True)
+    else:
+        for r in range(r0, r1):
+            dst[r, c0:c1].copy_(src[r, c0:c1], non_blocking=True)
+
+
+def to_host_overlapped(tensor, chunks):
+    """Blocks of a [nstars, nsamples] device tensor -> one NumPy array, copied block by block on a
+    side stream as soon as the kernel that produced each block has finished.  `chunks` is a list of
+    (row0, row1, col0, col1, event) with `event` recorded after that block's kernel: the D2H transfer of
+    block k overlaps the compute of blocks k+1.. (the copy engine and the SMs work concurrently)."""
+    t = torch()
+    cs = _copy_stream(tensor.device)
+    host = _host_result(tensor.shape, tensor.dtype)
     with t.cuda.stream(cs):
         for r0, r1, c0, c1, ev in chunks:
             cs.wait_event(ev)
-            host[r0:r1, c0:c1].copy_(tensor[r0:r1, c0:c1], non_blocking=True)
+            _copy_block(host, tensor, r0, r1, c0, c1)
     cs.synchronize()
     return host.numpy()
+
+
+def host_threads():
+    """Threads the host-side helpers of the library may use in this process: RVMC_HOST_THREADS, else the
+    cores this process may run on divided by the ranks sharing the node (LOCAL_WORLD_SIZE), at most 8."""
+    import os
+    env = os.environ.get("RVMC_HOST_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:          # pragma: no cover
+        cores = os.cpu_count() or 1
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(8, cores // local_world))
+
+
+def unpack_bits_overlapped(bits, n_cols, chunks, threads=None):
+    """Bit-packed flags [nrows, nwords] (int32 words on the device, bit j of word w = column 32 w + j) ->
+    NumPy bool [nrows, n_cols].  Block by block, as the kernels that produced them finish: the packed
+    block crosses PCIe on a side stream (1/8 of the bytes of a bool array) and is widened on the host by
+    rvmc_unpack_bits_host while later blocks are still being computed and copied.  `chunks` as for
+    to_host_overlapped (columns in flags, multiples of 32), or None for one block."""
+    t = torch()
+    lib = _abi.lib()
+    threads = host_threads() if threads is None else int(threads)
+    nrows, nwords = bits.shape
+    if chunks is None:
+        ev = t.cuda.Event()
+        ev.record(t.cuda.current_stream(bits.device))
+        chunks = [(0, nrows, 0, n_cols, ev)]
+    cs = _copy_stream(bits.device)
+    packed = t.empty(bits.shape, dtype=bits.dtype, pin_memory=True)
+    out = _host_result((nrows, n_cols), t.uint8)
+    done = []
+    with t.cuda.stream(cs):
+        for r0, r1, c0, c1, ev in chunks:
+            assert c0 % 32 == 0
+            cs.wait_event(ev)
+            _copy_block(packed, bits, r0, r1, c0 // 32, (c1 + 31) // 32)
+            e = t.cuda.Event()
+            e.record(cs)
+            done.append(e)
+    p_ptr, o_ptr = packed.data_ptr(), out.data_ptr()
+    for (r0, r1, c0, c1, _), e in zip(chunks, done):
+        e.synchronize()
+        _abi.check(lib.rvmc_unpack_bits_host(p_ptr + 4 * (r0 * nwords + c0 // 32), nwords, r1 - r0, c1 - c0,
+                                             o_ptr + r0 * n_cols + c0, n_cols, threads))
+    return out.numpy().view(np.bool_)
 
 
 def soa(**tensors):
@@ -148,6 +256,14 @@ def splitmix64(x):
     z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
     z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
     return z ^ (z >> 31)
+
+
+def call_seed(seed, call):
+    """Seed of the `call`-th random draw site of an object created with `seed`.  The user seed is hashed
+    once and the call counter enters through a multiplication by an odd constant in a DIFFERENT domain,
+    so objects created with neighbouring seeds (replicate studies over seed = 0..N) never walk into each
+    other's sequences -- with splitmix64(seed + call) object `s` at call k met object `s + 1` at call k - 1."""
+    return splitmix64(splitmix64(int(seed) & 0xFFFFFFFFFFFFFFFF) ^ ((int(call) * 0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF))
 
 
 def fresh_seed():

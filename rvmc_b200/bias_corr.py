@@ -17,6 +17,7 @@ reproduced by default; `physical_phase=True` uses 2 pi frac(t/P) instead.  Addit
 `seed`, `device`, `physical_phase`.
 """
 import ctypes as C
+import os
 import warnings
 
 import numpy as np
@@ -38,6 +39,10 @@ class BiasCorr(dv.LazyArrays):
     _ARRAY_ATTRS = _ORBIT + ("semi_major_axis", "max_orbital_velocity", "delta_rv", "delta_rv_single")
     # star ranges a large fused pass is launched in (the D2H copy of one range overlaps the next ranges)
     _d2h_chunks = 12
+    # how the detection flags of a fused pass travel to the host: "bits" = bit-packed by the kernel
+    # (one __ballot_sync word per warp, 1/8 of the PCIe bytes) and widened to NumPy bool on the host by
+    # the library's threaded helper; "bytes" = one uint8 per binary copied as is
+    flag_transfer = os.environ.get("RVMC_FLAG_TRANSFER", "bits")
 
     def __init__(self, t_obs, masses=None, mass_errors=None, number_of_samples=10**4, min_mass=6,
                  max_mass=20, min_period=10**0.15, max_period=10**3.5, period_pi=-0.5, mass_ratio_kappa=0,
@@ -146,7 +151,7 @@ class BiasCorr(dv.LazyArrays):
 
     # ---- plumbing -------------------------------------------------------------------------------
     def _next_seed(self):
-        s = dv.splitmix64((self.seed + self._calls) & 0xFFFFFFFFFFFFFFFF)
+        s = dv.call_seed(self.seed, self._calls)
         self._calls += 1
         return s
 
@@ -415,20 +420,20 @@ class BiasCorr(dv.LazyArrays):
         return dv.to_host(out)
 
     def check_error_shape(self, number_of_epochs):
-        """RVMC_bias_corr.py:374-393."""
-        if isinstance(self.rv_errors, (np.ndarray, list)):
-            if isinstance(self.rv_errors[self.current_star], (np.ndarray, list)):
-                if len(self.rv_errors[self.current_star]) == number_of_epochs:
-                    use_err = np.reshape(self.rv_errors[self.current_star], (-1, 1))
-                else:
-                    raise ValueError(f"The number of radial velocity uncertainties "
-                                     f"({len(self.rv_errors[self.current_star])}) does not match the number of epochs,"
-                                     f"({number_of_epochs})")
-            else:
-                use_err = self.rv_errors[self.current_star]
-        else:
-            use_err = self.rv_errors
-        return use_err
+        """The error(s) that apply to the current star (RVMC_bias_corr.py:374-393): the one number given
+        for everything, this star's number, or this star's per-epoch values as a column (n_epochs, 1)."""
+        sequence = (np.ndarray, list)
+        errors = self.rv_errors
+        if not isinstance(errors, sequence):
+            return errors
+        mine = errors[self.current_star]
+        if not isinstance(mine, sequence):
+            return mine
+        if len(mine) != number_of_epochs:
+            raise ValueError(f"The number of radial velocity uncertainties "
+                             f"({len(mine)}) does not match the number of epochs,"
+                             f"({number_of_epochs})")
+        return np.reshape(mine, (-1, 1))
 
     def generate_rv_errors(self, number_of_epochs, number_of_samples):
         """Fresh measurement errors for the current star, shape (n_epochs, n_samples) (:395-404)."""
@@ -473,7 +478,12 @@ class BiasCorr(dv.LazyArrays):
             self.calculate_max_orbital_velocity()
             return
         drv = dv.empty((nstars, ns), "float32", dev)
-        det = dv.empty((nstars, ns), "uint8", dev) if d_err is not None else None
+        det = bits = None
+        if d_err is not None:
+            if self.flag_transfer == "bits":
+                bits = dv.empty((nstars, (ns + 31) // 32), "int32", dev)
+            else:
+                det = dv.empty((nstars, ns), "uint8", dev)
         counters = dv.zeros((4,), "int64", dev)
         per_star = dv.zeros((max(nstars, 1),), "int32", dev)
         # large problems go out as a few launches over star ranges (sample ranges when there are only
@@ -495,7 +505,7 @@ class BiasCorr(dv.LazyArrays):
         chunks = []
         t = dv.torch()
         launch = self._fused_launcher(max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, None, counters,
-                                      per_star)
+                                      per_star, bits=bits)
         # the ranges are independent: they alternate between the current stream and a side stream, so the
         # draining tail of one launch is filled by the first blocks of the next
         main = t.cuda.current_stream(dev)
@@ -516,12 +526,12 @@ class BiasCorr(dv.LazyArrays):
             done.record(streams[1])
             main.wait_event(done)        # later work on the current stream sees every range
         self._rv_cache = dict(mode="fused", nep=nep, max_ep=max_ep, d_nep=d_nep, d_tobs=d_tobs, d_err=d_err,
-                              det={(float(delta_RV), float(n_sigma_RV)): (det, chunks)} if det is not None else {},
-                              counters=counters, per_star=per_star)
+                              det={(float(delta_RV), float(n_sigma_RV)): (det, bits, chunks)} if d_err is not None else {},
+                              counters=counters, per_star=per_star, pop=launch.pop, err_fp=self._errors_fingerprint())
         self._set_device("delta_rv", drv)
 
     def _fused_launcher(self, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
-                        per_star):
+                        per_star, bits=None, pop=None):
         """-> launch(s0, s1, stream, c0, c1): one rvmc_biascorr_fused call over stars [s0, s1) and samples
         [c0, c1) (default: all).  Population, mass tables
         and base pointers are resolved once; a star range is pointer arithmetic on the row-major
@@ -529,16 +539,18 @@ class BiasCorr(dv.LazyArrays):
         dev = self._device
         ns = int(self.number_of_samples)
         m, me = self._mass_tables()
-        pop = self._pop()
+        pop = self._pop() if pop is None else pop       # relaunches of a cached pass reuse ITS population
         lib = _abi.lib()
         quirk = 0 if self.physical_phase else 1
         stream = dv.stream_ptr(dev)
-        keep = (d_nep, d_tobs, d_err, m, me, drv, det, rv_out, counters, per_star, pop)
+        keep = (d_nep, d_tobs, d_err, m, me, drv, det, bits, rv_out, counters, per_star, pop)
 
         def base(x):
             return (0, 0) if x is None else (x.data_ptr(), x.stride(0) * x.element_size() if x.dim() else 0)
         b_nep, b_tobs, b_err, b_m, b_me = base(d_nep), base(d_tobs), base(d_err), base(m), base(me)
         b_drv, b_det, b_rv, b_star = base(drv), base(det), base(rv_out), base(per_star)
+        b_bits = base(bits)
+        bits_stride = 0 if bits is None else bits.stride(0)
         p_cnt = dv.ptr(counters)
         args = (float(delta_RV), float(n_sigma_RV))
 
@@ -550,19 +562,42 @@ class BiasCorr(dv.LazyArrays):
 
         def launch(s0, s1, stream=stream, c0=0, c1=ns, _keep=keep):
             # the sample index is the Philox counter, so a sample range reproduces the full pass bit for bit
-            _abi.check(lib.rvmc_biascorr_fused(
+            # (a sample range starts at a multiple of 32, so its flags start on a word of the packed rows)
+            _abi.check(lib.rvmc_biascorr_fused_packed(
                 C.byref(pop), self._seed0, self._rv_seed, s0, s1 - s0, max_ep, rows(b_nep, s0), rows(b_tobs, s0),
                 rows(b_err, s0), self._mass_mode, rows(b_m, s0), rows(b_me, s0), quirk, args[0], args[1], c0, c1 - c0,
-                ns, cols(b_drv, s0, c0, 4), cols(b_det, s0, c0, 1), cols(b_rv, s0, c0, 4), p_cnt, rows(b_star, s0),
-                stream))
+                ns, cols(b_drv, s0, c0, 4), cols(b_det, s0, c0, 1), cols(b_bits, s0, c0 // 32, 4), bits_stride,
+                cols(b_rv, s0, c0, 4), p_cnt, rows(b_star, s0), stream))
+        launch.pop = pop
         return launch
 
     def _launch_fused(self, nep, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
-                      per_star, stars=None):
+                      per_star, stars=None, bits=None, pop=None):
         s0, s1 = (0, self.number_of_stars) if stars is None else stars
         with dv.DeviceGuard(self._device):
             self._fused_launcher(max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
-                                 per_star)(int(s0), int(s1))
+                                 per_star, bits=bits, pop=pop)(int(s0), int(s1))
+
+    def _errors_fingerprint(self):
+        """The measurement errors AS THEY ARE NOW.  get_detected_binaries() compares it with the one taken
+        by calculate_radial_velocities(): the reference reads `self.rv_errors` again at :459-466, so a user
+        who edits the errors between the two calls gets thresholds from the new errors."""
+        e = self.__dict__.get("rv_errors", None)
+        if e is None:
+            return b""
+        try:
+            return np.asarray(e, dtype=np.float64).tobytes()
+        except (ValueError, TypeError):          # ragged per-epoch lists
+            return repr([list(np.ravel(x)) for x in e]).encode()
+
+    def _cached_rv_device(self, c):
+        """float32 [nstars, max_ep, ns] noisy RVs of the cached fused pass, regenerated from its own seeds,
+        population and error table (what the reference keeps in `radial_velocities`, :419-421)."""
+        nstars, ns = self.number_of_stars, int(self.number_of_samples)
+        rvd = dv.zeros((nstars, c["max_ep"], ns), "float32", self._device)
+        self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], 20, 4, None, None, rvd,
+                           None, None, pop=c["pop"])
+        return rvd
 
     def _radial_velocities_list(self):
         """`radial_velocities`: list of (n_epochs_i, n_samples) arrays (RVMC_bias_corr.py:250,419-421)."""
@@ -575,11 +610,7 @@ class BiasCorr(dv.LazyArrays):
             rv = dv.to_host(c["rv"])
         else:
             if "rv_host" not in c:
-                nstars, ns = self.number_of_stars, int(self.number_of_samples)
-                rvd = dv.zeros((nstars, c["max_ep"], ns), "float32", self._device)
-                self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], 20, 4, None, None, rvd,
-                                   None, None)
-                c["rv_host"] = dv.to_host(rvd).astype(np.float64)
+                c["rv_host"] = dv.to_host(self._cached_rv_device(c)).astype(np.float64)
             rv = c["rv_host"]
         out = [rv[i, :c["nep"][i]] for i in range(self.number_of_stars)]
         self._rv_user = out          # host copy is authoritative from now on (the user may edit it)
@@ -639,13 +670,35 @@ class BiasCorr(dv.LazyArrays):
                                                            float(delta_RV), float(n_sigma_RV), dv.ptr(det),
                                                            dv.stream_ptr(dev)))
             return dv.to_host(det).astype(bool)
-        if key not in c["det"]:
+        if c["err_fp"] != self._errors_fingerprint():
+            # rv_errors was edited after the pass: the reference applies the CURRENT errors to the RVs it
+            # stored (RVMC_bias_corr.py:459-466).  Same here: the RVs of the cached pass (its own noise) are
+            # regenerated and tested against thresholds from the current errors.  Rare path, fp64 test kernel.
+            _, max_ep2, _, _, d_err2 = self._tables()
+            if max_ep2 != c["max_ep"]:
+                raise ValueError("t_obs changed since calculate_radial_velocities()")
+            rv = self._cached_rv_device(c).double()
             det = dv.empty((nstars, ns), "uint8", dev)
+            with dv.DeviceGuard(dev):
+                _abi.check(_abi.lib().rvmc_biascorr_detect(nstars, ns, max_ep2, dv.ptr(c["d_nep"]), dv.ptr(rv),
+                                                           dv.ptr(d_err2), float(delta_RV), float(n_sigma_RV),
+                                                           dv.ptr(det), dv.stream_ptr(dev)))
+            return dv.to_host(det).view(np.bool_)
+        if key not in c["det"]:
+            det = bits = None
+            if self.flag_transfer == "bits":
+                bits = dv.empty((nstars, (ns + 31) // 32), "int32", dev)
+            else:
+                det = dv.empty((nstars, ns), "uint8", dev)
             self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], delta_RV, n_sigma_RV, None,
-                               det, None, None, None)
-            c["det"][key] = (det, None)
-        det, chunks = c["det"][key]
-        if chunks and len(chunks) > 1:
+                               det, None, None, None, bits=bits, pop=c["pop"])
+            c["det"][key] = (det, bits, None)
+        det, bits, chunks = c["det"][key]
+        if chunks is not None and len(chunks) < 2:
+            chunks = None
+        if bits is not None:
+            return dv.unpack_bits_overlapped(bits, ns, chunks)
+        if chunks:
             return dv.to_host_overlapped(det, chunks).view(np.bool_)
         return dv.to_host(det).view(np.bool_)
 

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(HERE, "librvmc_b200.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "build")
-SOURCES = ["abi_core.cu", "population.cu", "sigma_fused.cu", "biascorr.cu", "pipe_peaks.cu"]
+SOURCES = ["abi_core.cu", "population.cu", "sigma_fused.cu", "biascorr.cu", "pipe_peaks.cu", "host_bits.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-I", INCLUDE]
@@ -27,7 +27,7 @@ def _nvcc():
 
 
 def _deps():
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
     files += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
     files.append(os.path.abspath(__file__))
     return files
@@ -64,7 +64,7 @@ def _build(force, verbose, defines):
     extra = (["-Xptxas", "-v"] if verbose else []) + list(defines)
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
@@ -77,7 +77,7 @@ def _build(force, verbose, defines):
         for _, log in results:
             sys.stderr.write(log)
     tmp = OUT + ".tmp"
-    cmd = [nvcc, "-shared", "-o", tmp, "-gencode", "arch=compute_100a,code=sm_100a"] + [o for o, _ in results]
+    cmd = [nvcc, "-shared", "-o", tmp, "-gencode", "arch=compute_100a,code=sm_100a"] + [o for o, _ in results] + ["-lpthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)

@@ -49,6 +49,8 @@ struct BcArgs {
     int64_t n_samples, sample_stride;
     float* delta_rv;              // [nstars][sample_stride]
     uint8_t* detected;            // [nstars][sample_stride]
+    uint32_t* det_bits;           // [nstars][bits_stride]: the same flags, one bit per sample (ballot words)
+    int64_t bits_stride;
     float* rv_out;                // [nstars][max_epochs][sample_stride]
     unsigned long long* counters; // [4]: binary-epoch RVs, detected, guard, non-converged
     uint32_t* det_per_star;       // [nstars]
@@ -138,12 +140,17 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
     __syncthreads();
 
     unsigned int my_guard = 0, my_bad = 0, my_det = 0;
+    const int lane = threadIdx.x & 31;
     const int64_t i_first = (int64_t)blockIdx.x * (BC_THREADS * a.spt) + threadIdx.x;
 #pragma unroll 1
     for (int rep = 0; rep < a.spt; ++rep) {
         const int64_t i = i_first + (int64_t)rep * BC_THREADS;
-        if (i >= a.n_samples) break;
-        const uint64_t sample = a.first_sample + (uint64_t)i;
+        // A warp covers 32 consecutive samples and leaves the loop as a whole (its flags go out as one
+        // ballot word).  Lanes past the end of a ragged last warp recompute the last sample and store
+        // nothing.
+        if (i - lane >= a.n_samples) break;
+        const bool valid = i < a.n_samples;
+        const uint64_t sample = a.first_sample + (uint64_t)(valid ? i : a.n_samples - 1);
         const uint64_t item = bc_item(a.first_star + star, sample);
         const u32x4 wa = philox_block(a.key, item, RVMC_STREAM_ORBIT_A, 0);
         const u32x4 wb = philox_block(a.key, item, RVMC_STREAM_ORBIT_B, 0);
@@ -205,6 +212,7 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
         float rvs[NE];
         float vmax = -INFINITY, vmin = INFINITY;
         float z[6];
+        unsigned int s_guard = 0, s_bad = 0;
         auto epoch = [&](int k) {
             if (noisy && (k % 6) == 0) bc_noise6_f32(a.noise_key, item, RVMC_STREAM_EPOCH, k / 6, z);
             float M;
@@ -226,13 +234,13 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
             // K is folded into the orientation terms (the shape is linear in sin/cos omega)
             float rv = kepler_shape_f32<ITERS, GUARD>(M, M64, neg, o.e, rome2, Ksw, Kcw, a.kepler_iters,
                                                       a.P32.guard_amp, g, b);
-            my_guard += g;
-            my_bad += b;
+            s_guard += g;
+            s_bad += b;
             if (noisy) rv = fmaf(err_s[k], z[k % 6], rv);
             rvs[k] = rv;
             vmax = fmaxf(vmax, rv);
             vmin = fminf(vmin, rv);
-            if (rv_out) rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
+            if (rv_out && valid) rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
         };
         if constexpr (NE <= 16) {
             // fully unrolled: rvs[] and z[] live in registers; a star with exactly NE epochs (the common
@@ -249,10 +257,14 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
 #pragma unroll 1
             for (int k = 0; k < ne; ++k) epoch(k);
         }
+        if (valid) {
+            my_guard += s_guard;
+            my_bad += s_bad;
+        }
         // np.max/np.min propagate NaN (mass draw <= 0, Q12); fmaxf/fminf would drop it
         float drv = vmax - vmin;
         if (K != K) drv = K;
-        if (a.delta_rv) a.delta_rv[(size_t)star * a.sample_stride + i] = drv;
+        if (a.delta_rv && valid) a.delta_rv[(size_t)star * a.sample_stride + i] = drv;
 
         // ---- significance test --------------------------------------------------------------------
         bool det = false;
@@ -271,7 +283,13 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
                     for (int y = x + 1; y < ne; ++y) det = det || (fabsf(rvs[x] - rvs[y]) > thr_s[x * NE + y]);
             }
         }
-        if (a.detected) a.detected[(size_t)star * a.sample_stride + i] = det ? 1 : 0;
+        det = det && valid;
+        if (a.detected && valid) a.detected[(size_t)star * a.sample_stride + i] = det ? 1 : 0;
+        if (a.det_bits) {
+            // RVMC_bias_corr.py:476 returns one bool per binary: one bit of it leaves the chip
+            const unsigned int word = __ballot_sync(0xffffffffu, det);
+            if (lane == 0) a.det_bits[(size_t)star * a.bits_stride + (i >> 5)] = word;
+        }
         my_det += det ? 1u : 0u;
     }
 
@@ -500,12 +518,27 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
                         float n_sigma, uint64_t first_sample, int64_t n_samples, int64_t sample_stride,
                         float* delta_rv, uint8_t* detected, float* rv_out, uint64_t* counters,
                         uint32_t* det_per_star, void* cuda_stream) {
+    return rvmc_biascorr_fused_packed(p, seed, noise_seed, first_star, nstars, max_epochs, n_epochs, t_obs, rv_err,
+                                      mass_mode, masses, mass_errors, quirk_phase, delta_rv_min, n_sigma, first_sample,
+                                      n_samples, sample_stride, delta_rv, detected, nullptr, 0, rv_out, counters,
+                                      det_per_star, cuda_stream);
+}
+
+int rvmc_biascorr_fused_packed(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int first_star,
+                               int nstars, int max_epochs, const int32_t* n_epochs, const double* t_obs,
+                               const float* rv_err, int mass_mode, const double* masses, const double* mass_errors,
+                               int quirk_phase, float delta_rv_min, float n_sigma, uint64_t first_sample,
+                               int64_t n_samples, int64_t sample_stride, float* delta_rv, uint8_t* detected,
+                               uint32_t* detected_bits, int64_t bits_stride, float* rv_out, uint64_t* counters,
+                               uint32_t* det_per_star, void* cuda_stream) {
     RVMC_DEVICE_GATE();
     int rc = bc_check_common(p, nstars, max_epochs, n_epochs);
     if (rc) return rc;
     RVMC_REQUIRE(n_samples >= 0, "number_of_samples must be >= 0");
     RVMC_REQUIRE(first_star >= 0 && (int64_t)first_star + nstars <= (1 << 24), "star index must stay below 2^24");
     RVMC_REQUIRE(sample_stride >= n_samples, "sample_stride must be >= n_samples");
+    RVMC_REQUIRE(detected_bits == nullptr || bits_stride >= (n_samples + 31) / 32,
+                 "bits_stride must be >= ceil(n_samples / 32) words");
     RVMC_REQUIRE(mass_mode >= 0 && mass_mode <= 2, "mass_mode must be 0, 1 or 2");
     RVMC_REQUIRE(mass_mode == 0 || masses != nullptr, "masses are required for mass_mode %d", mass_mode);
     RVMC_REQUIRE(mass_mode != 1 || mass_errors != nullptr, "mass_errors are required for mass_mode 1");
@@ -546,6 +579,8 @@ int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_
     a.sample_stride = sample_stride;
     a.delta_rv = delta_rv;
     a.detected = detected;
+    a.det_bits = detected_bits;
+    a.bits_stride = bits_stride;
     a.rv_out = rv_out;
     a.counters = (unsigned long long*)counters;
     a.det_per_star = det_per_star;

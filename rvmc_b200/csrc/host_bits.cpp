@@ -1,0 +1,285 @@
+// Host-side companion of the bit-packed detection output (rvmc_biascorr_fused_packed): expands the
+// packed words into the bool array get_detected_binaries returns (RVMC_bias_corr.py:451-476 hands
+// back `detected`, dtype bool, shape (n_stars, n_samples)) with a small persistent thread pool.
+//
+// Why it exists: one detection flag per binary is 1 byte in the reference's result but 1 BIT of
+// information.  Shipping bytes over PCIe makes the device-to-host copy the slowest stage of the
+// end-to-end pass (100 MB per 10^8 binaries against a 3 ms kernel); shipping bits and widening them
+// where the result is consumed moves 8x less over the link.  No GPU work happens here and nothing of
+// the Monte-Carlo arithmetic either: this is the tail end of a copy.
+//
+// Bit order: bit j of word w of a row is column 32 w + j (what __ballot_sync produces for 32
+// consecutive samples).  On a little-endian host the words are a byte stream in which bit j of byte
+// k is column 8 k + j, i.e. np.unpackbits(..., bitorder="little").
+#include <emmintrin.h>   // SSE2: baseline of every x86-64 CPU (streaming stores)
+#include <pthread.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/rvmc_b200.h"
+
+namespace rvmc {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+// ---- a minimal persistent fork-join pool ----------------------------------------------------------
+// parallel_for(n_tasks, n_threads, fn): tasks are claimed from an atomic counter by up to
+// n_threads - 1 pool workers plus the calling thread.  One job at a time (callers serialise on
+// run_mu); workers sleep on a condition variable between jobs.
+class Pool {
+  public:
+    typedef void (*TaskFn)(void* ctx, int64_t task);
+
+    void run(int64_t n_tasks, int n_threads, TaskFn fn, void* ctx) {
+        if (n_tasks <= 0) return;
+        if (n_threads > (int)n_tasks) n_threads = (int)n_tasks;
+        if (n_threads <= 1) {
+            for (int64_t t = 0; t < n_tasks; ++t) fn(ctx, t);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(run_mu_);
+        grow(n_threads - 1);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = fn;
+            ctx_ = ctx;
+            n_tasks_ = n_tasks;
+            next_.store(0, std::memory_order_relaxed);
+            wanted_ = n_threads - 1;
+            running_ = 0;
+            ++generation_;
+        }
+        cv_job_.notify_all();
+        drain(fn, ctx, n_tasks);
+        std::unique_lock<std::mutex> lk(mu_);
+        wanted_ = 0;                                        // late wakers find nothing to join
+        cv_done_.wait(lk, [this] { return running_ == 0; });
+    }
+
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            ++generation_;
+        }
+        cv_job_.notify_all();
+        for (auto& t : workers_)
+            if (t.joinable()) t.join();
+    }
+
+  private:
+    void drain(TaskFn fn, void* ctx, int64_t n_tasks) {
+        for (;;) {
+            const int64_t t = next_.fetch_add(1, std::memory_order_relaxed);
+            if (t >= n_tasks) break;
+            fn(ctx, t);
+        }
+    }
+
+    void grow(int n) {
+        while ((int)workers_.size() < n) workers_.emplace_back([this] { worker(); });
+    }
+
+    void worker() {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_job_.wait(lk, [&] { return generation_ != seen; });
+            seen = generation_;
+            if (stop_) return;
+            if (wanted_ <= 0) continue;
+            --wanted_;
+            ++running_;
+            TaskFn fn = fn_;
+            void* ctx = ctx_;
+            const int64_t n = n_tasks_;
+            lk.unlock();
+            drain(fn, ctx, n);
+            lk.lock();
+            if (--running_ == 0) cv_done_.notify_all();
+        }
+    }
+
+    std::mutex run_mu_, mu_;
+    std::condition_variable cv_job_, cv_done_;
+    std::vector<std::thread> workers_;
+    TaskFn fn_ = nullptr;
+    void* ctx_ = nullptr;
+    int64_t n_tasks_ = 0;
+    std::atomic<int64_t> next_{0};
+    int wanted_ = 0, running_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
+std::atomic<Pool*> g_pool{nullptr};
+std::atomic<bool> g_atfork_registered{false};
+
+void pool_child_after_fork() {
+    // the child gets a fresh pool on first use; the parent's object (its mutexes possibly held by
+    // threads that do not exist here) is leaked on purpose
+    g_pool.store(nullptr, std::memory_order_release);
+}
+
+// The pool lives until the process ends (never destroyed: its sleeping workers die with the process).
+Pool& pool() {
+    Pool* p = g_pool.load(std::memory_order_acquire);
+    if (!p) {
+        Pool* fresh = new Pool();
+        if (g_pool.compare_exchange_strong(p, fresh, std::memory_order_acq_rel)) {
+            p = fresh;
+            if (!g_atfork_registered.exchange(true)) pthread_atfork(nullptr, nullptr, pool_child_after_fork);
+        } else {
+            delete fresh;       // another thread won the race; `fresh` never started a worker
+        }
+    }
+    return *p;
+}
+
+// ---- bit -> byte expansion --------------------------------------------------------------------------
+uint64_t g_lut[256];
+std::once_flag g_lut_once;
+
+void build_lut() {
+    for (int b = 0; b < 256; ++b) {
+        uint64_t v = 0;
+        for (int j = 0; j < 8; ++j)
+            if (b & (1 << j)) v |= (uint64_t)1 << (8 * j);
+        g_lut[b] = v;
+    }
+}
+
+// n_cols flags of one row: src = packed bytes (column 0 is bit 0 of src[0]), dst = n_cols bytes of 0/1.
+void expand_row(const uint8_t* src, uint8_t* dst, int64_t n_cols) {
+    int64_t c = 0;
+    const int64_t full = n_cols & ~(int64_t)7;
+    // head: up to the first 16-byte boundary of dst, in whole source bytes
+    while (c < full && ((uintptr_t)(dst + c) & 15)) {
+        const uint64_t v = g_lut[src[c >> 3]];
+        memcpy(dst + c, &v, 8);
+        c += 8;
+    }
+    // body: two source bytes -> one 16-byte streaming store (the result is written once and read later
+    // by somebody else: no reason to pull the destination lines into this core's cache first)
+    for (; c + 16 <= full; c += 16) {
+        const __m128i v = _mm_set_epi64x((long long)g_lut[src[(c >> 3) + 1]], (long long)g_lut[src[c >> 3]]);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + c), v);
+    }
+    for (; c < full; c += 8) {
+        const uint64_t v = g_lut[src[c >> 3]];
+        memcpy(dst + c, &v, 8);
+    }
+    if (c < n_cols) {
+        const uint64_t v = g_lut[src[c >> 3]];
+        memcpy(dst + c, &v, (size_t)(n_cols - c));
+    }
+}
+
+struct UnpackJob {
+    const uint8_t* bits;
+    int64_t bits_stride_bytes;
+    uint8_t* out;
+    int64_t out_stride;
+    int64_t n_cols;
+    int64_t segs_per_row;
+    int64_t seg_cols;          // multiple of 64
+};
+
+void unpack_task(void* ctx, int64_t task) {
+    const UnpackJob& j = *static_cast<const UnpackJob*>(ctx);
+    const int64_t row = task / j.segs_per_row;
+    const int64_t c0 = (task - row * j.segs_per_row) * j.seg_cols;
+    const int64_t n = (j.n_cols - c0 < j.seg_cols) ? j.n_cols - c0 : j.seg_cols;
+    expand_row(j.bits + row * j.bits_stride_bytes + (c0 >> 3), j.out + row * j.out_stride + c0, n);
+    _mm_sfence();
+}
+
+struct CountJob {
+    const uint32_t* bits;
+    int64_t bits_stride;
+    int64_t n_cols;
+    int64_t* counts;
+};
+
+void count_task(void* ctx, int64_t row) {
+    const CountJob& j = *static_cast<const CountJob*>(ctx);
+    const uint32_t* w = j.bits + row * j.bits_stride;
+    const int64_t full = j.n_cols >> 5;
+    int64_t n = 0;
+    for (int64_t k = 0; k < full; ++k) n += __builtin_popcount(w[k]);
+    const int rem = (int)(j.n_cols & 31);
+    if (rem) n += __builtin_popcount(w[full] & ((1u << rem) - 1u));
+    j.counts[row] = n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rvmc_unpack_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, int64_t n_rows, int64_t n_cols,
+                          uint8_t* out_host, int64_t out_stride, int n_threads) {
+    if (n_rows < 0 || n_cols < 0) {
+        rvmc::set_error("rvmc_unpack_bits_host: negative shape");
+        return RVMC_ERR_INVALID;
+    }
+    if (n_rows == 0 || n_cols == 0) return RVMC_OK;
+    if (!bits_host || !out_host) {
+        rvmc::set_error("rvmc_unpack_bits_host: bits_host and out_host are required");
+        return RVMC_ERR_INVALID;
+    }
+    if (bits_stride_words < (n_cols + 31) / 32 || out_stride < n_cols) {
+        rvmc::set_error("rvmc_unpack_bits_host: a row stride is shorter than the row");
+        return RVMC_ERR_INVALID;
+    }
+    std::call_once(g_lut_once, build_lut);
+    UnpackJob j;
+    j.bits = reinterpret_cast<const uint8_t*>(bits_host);
+    j.bits_stride_bytes = bits_stride_words * 4;
+    j.out = out_host;
+    j.out_stride = out_stride;
+    j.n_cols = n_cols;
+    // tasks of at most 256 Ki flags (32 KB in, 256 KB out): fine-grained enough to balance a few
+    // threads over one long row, coarse enough that claiming a task costs nothing
+    j.seg_cols = 262144;
+    j.segs_per_row = (n_cols + j.seg_cols - 1) / j.seg_cols;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    pool().run(n_rows * j.segs_per_row, n_threads, unpack_task, &j);
+    return RVMC_OK;
+}
+
+int rvmc_count_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, int64_t n_rows, int64_t n_cols,
+                         int64_t* counts_host, int n_threads) {
+    if (n_rows < 0 || n_cols < 0) {
+        rvmc::set_error("rvmc_count_bits_host: negative shape");
+        return RVMC_ERR_INVALID;
+    }
+    if (n_rows == 0) return RVMC_OK;
+    if (!bits_host || !counts_host) {
+        rvmc::set_error("rvmc_count_bits_host: bits_host and counts_host are required");
+        return RVMC_ERR_INVALID;
+    }
+    if (bits_stride_words < (n_cols + 31) / 32) {
+        rvmc::set_error("rvmc_count_bits_host: the row stride is shorter than the row");
+        return RVMC_ERR_INVALID;
+    }
+    CountJob j;
+    j.bits = bits_host;
+    j.bits_stride = bits_stride_words;
+    j.n_cols = n_cols;
+    j.counts = counts_host;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    pool().run(n_rows, n_threads, count_task, &j);
+    return RVMC_OK;
+}
+
+}  // extern "C"

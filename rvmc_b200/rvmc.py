@@ -117,7 +117,7 @@ class RVMC(dv.LazyArrays):
 
     # ---- helpers --------------------------------------------------------------------------------
     def _next_seed(self):
-        s = dv.splitmix64((self.seed + self._calls) & 0xFFFFFFFFFFFFFFFF)
+        s = dv.call_seed(self.seed, self._calls)
         self._calls += 1
         return s
 

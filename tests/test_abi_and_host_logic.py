@@ -65,7 +65,7 @@ def test_defaults_match_reference_constructor(lib):
     assert (p.min_mass, p.max_mass, p.mass_power, p.period_pi, p.mass_ratio_kappa, p.e_power) == (6, 20, -2.35, -0.5, 0, -0.5)
     assert (p.min_period, p.max_period) == (10 ** 0.15, 10 ** 3.5) and (p.sigma_dyn, p.fbin) == (2.0, 0.7)
     assert (p.e_min, p.e_max_mid, p.e_max_long, p.p_circ_days, p.p_mid_days) == (1e-5, 0.5, 0.9, 4.0, 6.0)
-    assert lib.rvmc_abi_version() == 1
+    assert lib.rvmc_abi_version() == 2
 
 
 def test_no_gpu_means_loud_failure_not_fallback(lib):
@@ -250,3 +250,50 @@ def test_hot_kernels_resource_usage_and_instruction_mix(lib):
     assert "IMAD.WIDE.U32" in sass and "MUFU.EX2" in sass and "MUFU.LG2" in sass and "DFMA" in sass
     for tensor_op in ("HMMA", "UTCHMMA", "UTCQMMA", "IMMA", "DMMA"):
         assert tensor_op not in sass, tensor_op
+
+
+def test_host_bit_helpers_match_numpy_unpackbits():
+    """rvmc_unpack_bits_host / rvmc_count_bits_host are host code: checked here against NumPy for ragged
+    widths, strides wider than the row, sub-blocks of a larger array and several thread counts."""
+    lib = _abi.lib()
+    rng = np.random.default_rng(3)
+    for nr, nc, threads in [(1, 1, 1), (3, 100, 1), (5, 300_007, 4), (1, 64, 2), (7, 31, 3), (2, 4096 * 3 + 5, 8),
+                            (4, 262144 * 2 + 17, 5)]:
+        nw = (nc + 31) // 32 + 2
+        bits = rng.integers(0, 2 ** 32, size=(nr, nw), dtype=np.uint32)
+        out = np.full((nr, nc + 5), 7, np.uint8)
+        assert lib.rvmc_unpack_bits_host(bits.ctypes.data, nw, nr, nc, out.ctypes.data, nc + 5, threads) == 0
+        want = np.unpackbits(bits.view(np.uint8).reshape(nr, -1), axis=1, bitorder="little")[:, :nc]
+        np.testing.assert_array_equal(out[:, :nc], want)
+        assert (out[:, nc:] == 7).all()                        # nothing written past the row
+        counts = np.zeros(nr, np.int64)
+        assert lib.rvmc_count_bits_host(bits.ctypes.data, nw, nr, nc, counts.ctypes.data, threads) == 0
+        np.testing.assert_array_equal(counts, want.sum(axis=1))
+    # a sub-block: rows 1..2, columns 64..(64+1000) of a 4-row array
+    nr, nc = 4, 5000
+    nw = (nc + 31) // 32
+    bits = rng.integers(0, 2 ** 32, size=(nr, nw), dtype=np.uint32)
+    out = np.zeros((nr, nc), np.uint8)
+    assert lib.rvmc_unpack_bits_host(bits.ctypes.data + 4 * (1 * nw + 2), nw, 2, 1000, out.ctypes.data + nc + 64, nc,
+                                     2) == 0
+    want = np.unpackbits(bits.view(np.uint8).reshape(nr, -1), axis=1, bitorder="little")[:, :nc]
+    np.testing.assert_array_equal(out[1:3, 64:1064], want[1:3, 64:1064])
+    assert out.sum() == want[1:3, 64:1064].sum()
+    # argument errors
+    assert lib.rvmc_unpack_bits_host(bits.ctypes.data, 1, nr, nc, out.ctypes.data, nc, 1) == _abi.RVMC_ERR_INVALID
+    assert lib.rvmc_unpack_bits_host(None, nw, nr, nc, out.ctypes.data, nc, 1) == _abi.RVMC_ERR_INVALID
+
+
+def test_call_seeds_of_neighbouring_user_seeds_are_disjoint():
+    """with splitmix64(seed + call) object `s` at call k reused the seed of object s+1 at call
+    k-1 (replicate studies over seed = 0..N were silently correlated).  The call counter now enters in a
+    different domain: the sequences of 64 neighbouring seeds over 64 calls do not share a single value."""
+    from rvmc_b200._device import call_seed
+    seen = {}
+    for s in list(range(64)) + [2 ** 64 - 1, 2 ** 63, 1234, 1235]:
+        for k in range(64):
+            v = call_seed(s, k)
+            assert 0 <= v < 2 ** 64
+            assert v not in seen, (s, k, seen[v])
+            seen[v] = (s, k)
+    assert call_seed(5, 3) == call_seed(5 + 2 ** 64, 3)           # the seed is taken mod 2^64

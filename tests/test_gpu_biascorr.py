@@ -371,3 +371,94 @@ def test_random_campaigns_fused_vs_oracle(trial):
             want_det = np.zeros(ns, dtype=bool)
         assert (want_det != noisy["det"][i]).sum() <= max(1, ns // 2000), (trial, i)
     assert noisy["cnt"][0] == ns * int(neps.sum()) and noisy["cnt"][3] == 0
+
+
+@pytest.mark.parametrize("ns", [1000, 4099, 32 * 300])
+def test_packed_detection_flags_equal_the_byte_flags(ns):
+    """rvmc_biascorr_fused_packed: bit j of word w of a star's row is the uint8 flag of sample 32 w + j
+    (ragged last warps included), whole pass and sample shards starting at multiples of 32; the host
+    helper widens them to the bool array of RVMC_bias_corr.py:476 and counts them per star."""
+    p = _abi.PopParams.defaults()
+    rng = np.random.RandomState(4)
+    t_obs = [DAYS6, np.sort(rng.uniform(0, np.pi * 1e7, 5)), DAYS6[:4]]
+    errs = [2.0, [1.0, 2.0, 3.0, 1.5, 0.5], 1.2]
+    nstars = len(t_obs)
+    nep, max_ep, d_nep, d_tobs, d_err = _tables(t_obs, errs)
+    nw = (ns + 31) // 32 + 1                                   # a stride wider than the row
+    det = g.empty((nstars, ns), "uint8")
+    drv = g.empty((nstars, ns), "float32")
+    bits = g.zeros((nstars, nw), "int32")
+    cnt = g.zeros((4,), "int64")
+
+    def run(c0, c1, det_t, bits_t, drv_t):
+        g.ok(g.lib().rvmc_biascorr_fused_packed(
+            C.byref(p), 11, 12, 0, nstars, max_ep, dv.ptr(d_nep), dv.ptr(d_tobs), dv.ptr(d_err), 0, None, None, 1, 20.0,
+            4.0, c0, c1 - c0, ns, None if drv_t is None else drv_t.data_ptr() + 4 * c0,
+            None if det_t is None else det_t.data_ptr() + c0, bits_t.data_ptr() + 4 * (c0 // 32), nw, None,
+            dv.ptr(cnt), None, g.stream()))
+
+    run(0, ns, det, bits, drv)
+    want = g.host(det).astype(bool)
+    assert 0.05 < want.mean() < 0.95
+    hb = g.host(bits).view(np.uint32)
+    got = np.unpackbits(hb.view(np.uint8).reshape(nstars, -1), axis=1, bitorder="little")[:, :ns].astype(bool)
+    np.testing.assert_array_equal(got, want)
+    assert int(g.host(cnt)[1]) == int(want.sum())
+    # bits past the end of a ragged row are zero (invalid lanes vote 0)
+    full = np.unpackbits(hb.view(np.uint8).reshape(nstars, -1), axis=1, bitorder="little")
+    assert not full[:, ns:32 * ((ns + 31) // 32)].any()
+    # the library's host helper: widening and per-row counts
+    out = np.full((nstars, ns), 9, dtype=np.uint8)
+    hb = np.ascontiguousarray(hb)
+    g.ok(g.lib().rvmc_unpack_bits_host(hb.ctypes.data, nw, nstars, ns, out.ctypes.data, ns, 3))
+    np.testing.assert_array_equal(out.view(np.bool_), want)
+    counts = np.zeros(nstars, dtype=np.int64)
+    g.ok(g.lib().rvmc_count_bits_host(hb.ctypes.data, nw, nstars, ns, counts.ctypes.data, 2))
+    np.testing.assert_array_equal(counts, want.sum(axis=1))
+    # sample shards (the e2e path launches these on two streams): same bits, same Delta-RV
+    bits2 = g.zeros((nstars, nw), "int32")
+    drv2 = g.empty((nstars, ns), "float32")
+    cuts = [0, 32 * 7, 32 * 20, ns]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        run(a, b, None, bits2, drv2)
+    np.testing.assert_array_equal(g.host(bits2), g.host(bits))
+    np.testing.assert_array_equal(g.host(drv2), g.host(drv))
+
+
+@pytest.mark.parametrize("transfer", ["bits", "bytes"])
+def test_biascorr_class_flag_transfer_modes_agree(transfer, monkeypatch):
+    """get_detected_binaries() through the class: the bit-packed route (default) and the byte route give
+    the same bool array; large enough that the pass is launched in overlapped ranges."""
+    from rvmc_b200.bias_corr import BiasCorr
+    res = {}
+    for mode in ("bits", "bytes"):
+        monkeypatch.setattr(BiasCorr, "flag_transfer", mode)
+        for shape in ((40, 110_000), (2, 2_100_000)):
+            bc = BiasCorr([DAYS6] * shape[0], number_of_samples=shape[1], rv_errors=2.0, seed=5)
+            bc.calculate_radial_velocities()
+            d = bc.get_detected_binaries()
+            assert d.dtype == np.bool_ and d.shape == shape
+            res[(mode, shape)] = d
+            per_star, counters = bc.detection_counts()
+            np.testing.assert_array_equal(per_star, d.sum(axis=1))
+            d2 = bc.get_detected_binaries(delta_RV=30, n_sigma_RV=3)        # relaunch for another key
+            assert d2.shape == shape and d2.sum() < d.sum()
+    for shape in ((40, 110_000), (2, 2_100_000)):
+        np.testing.assert_array_equal(res[("bits", shape)], res[("bytes", shape)])
+
+
+def test_editing_rv_errors_after_the_pass_changes_only_the_thresholds():
+    """RVMC_bias_corr.py:459-466 reads self.rv_errors when get_detected_binaries() runs: the stored RVs
+    (noise from the OLD errors) are tested against thresholds from the NEW errors."""
+    from rvmc_b200.bias_corr import BiasCorr
+    bc = BiasCorr([DAYS6] * 3, number_of_samples=4000, rv_errors=2.0, seed=9)
+    bc.calculate_radial_velocities()
+    d_old = bc.get_detected_binaries()
+    rv = [np.array(r) for r in bc.radial_velocities]
+    bc2 = BiasCorr([DAYS6] * 3, number_of_samples=4000, rv_errors=2.0, seed=9)
+    bc2.calculate_radial_velocities()
+    bc2.rv_errors = 8.0
+    d_new = bc2.get_detected_binaries()
+    want = np.stack([orc.detected_binaries(rv[i], 8.0, 20, 4) for i in range(3)])
+    assert (d_new != want).sum() <= 2                       # fp32 RVs at the threshold
+    assert d_new.sum() < d_old.sum()
