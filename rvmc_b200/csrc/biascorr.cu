@@ -145,12 +145,8 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
 #pragma unroll 1
     for (int rep = 0; rep < a.spt; ++rep) {
         const int64_t i = i_first + (int64_t)rep * BC_THREADS;
-        // A warp covers 32 consecutive samples and leaves the loop as a whole (its flags go out as one
-        // ballot word).  Lanes past the end of a ragged last warp recompute the last sample and store
-        // nothing.
-        if (i - lane >= a.n_samples) break;
-        const bool valid = i < a.n_samples;
-        const uint64_t sample = a.first_sample + (uint64_t)(valid ? i : a.n_samples - 1);
+        if (i >= a.n_samples) break;
+        const uint64_t sample = a.first_sample + (uint64_t)i;
         const uint64_t item = bc_item(a.first_star + star, sample);
         const u32x4 wa = philox_block(a.key, item, RVMC_STREAM_ORBIT_A, 0);
         const u32x4 wb = philox_block(a.key, item, RVMC_STREAM_ORBIT_B, 0);
@@ -212,7 +208,6 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
         float rvs[NE];
         float vmax = -INFINITY, vmin = INFINITY;
         float z[6];
-        unsigned int s_guard = 0, s_bad = 0;
         auto epoch = [&](int k) {
             if (noisy && (k % 6) == 0) bc_noise6_f32(a.noise_key, item, RVMC_STREAM_EPOCH, k / 6, z);
             float M;
@@ -234,13 +229,13 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
             // K is folded into the orientation terms (the shape is linear in sin/cos omega)
             float rv = kepler_shape_f32<ITERS, GUARD>(M, M64, neg, o.e, rome2, Ksw, Kcw, a.kepler_iters,
                                                       a.P32.guard_amp, g, b);
-            s_guard += g;
-            s_bad += b;
+            my_guard += g;
+            my_bad += b;
             if (noisy) rv = fmaf(err_s[k], z[k % 6], rv);
             rvs[k] = rv;
             vmax = fmaxf(vmax, rv);
             vmin = fminf(vmin, rv);
-            if (rv_out && valid) rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
+            if (rv_out) rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
         };
         if constexpr (NE <= 16) {
             // fully unrolled: rvs[] and z[] live in registers; a star with exactly NE epochs (the common
@@ -257,14 +252,10 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
 #pragma unroll 1
             for (int k = 0; k < ne; ++k) epoch(k);
         }
-        if (valid) {
-            my_guard += s_guard;
-            my_bad += s_bad;
-        }
         // np.max/np.min propagate NaN (mass draw <= 0, Q12); fmaxf/fminf would drop it
         float drv = vmax - vmin;
         if (K != K) drv = K;
-        if (a.delta_rv && valid) a.delta_rv[(size_t)star * a.sample_stride + i] = drv;
+        if (a.delta_rv) a.delta_rv[(size_t)star * a.sample_stride + i] = drv;
 
         // ---- significance test --------------------------------------------------------------------
         bool det = false;
@@ -283,11 +274,15 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
                     for (int y = x + 1; y < ne; ++y) det = det || (fabsf(rvs[x] - rvs[y]) > thr_s[x * NE + y]);
             }
         }
-        det = det && valid;
-        if (a.detected && valid) a.detected[(size_t)star * a.sample_stride + i] = det ? 1 : 0;
+        if (a.detected) a.detected[(size_t)star * a.sample_stride + i] = det ? 1 : 0;
         if (a.det_bits) {
-            // RVMC_bias_corr.py:476 returns one bool per binary: one bit of it leaves the chip
-            const unsigned int word = __ballot_sync(0xffffffffu, det);
+            // RVMC_bias_corr.py:476 returns one bool per binary: one BIT of it leaves the chip.  A warp holds
+            // 32 consecutive samples; the lanes past the end of a ragged last warp have left the loop and are
+            // not named in the mask, so their bits are 0.
+            const int64_t left = a.n_samples - (i - lane);          // warp-uniform
+            unsigned int word;
+            if (left >= 32) word = __ballot_sync(0xffffffffu, det);
+            else word = __ballot_sync((1u << (int)left) - 1u, det);   // a computed mask costs ~30 instructions: tail only
             if (lane == 0) a.det_bits[(size_t)star * a.bits_stride + (i >> 5)] = word;
         }
         my_det += det ? 1u : 0u;

@@ -45,6 +45,7 @@ struct FusedArgs {
     const float* meas_err;     // device [S]
     float* sigma_out;          // [n_points][sigma_stride]
     unsigned long long* counters;   // [4] or nullptr: binary RVs, guard lanes, non-converged lanes
+    uint32_t* fail;                 // [rows][2] or nullptr: per grid point {guard lanes, non-converged lanes}
     uint64_t first_real;
     int64_t n_real;            // realizations per point
     int64_t sigma_stride;
@@ -196,6 +197,12 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
         if (cnt_guard) atomicAdd(a.counters + 1, (unsigned long long)cnt_guard);
         if (cnt_bad) atomicAdd(a.counters + 2, (unsigned long long)cnt_bad);
     }
+    // per-point failure counts (rvmc_point_stats.n_guard / n_nonconverged): what scipy.optimize.newton
+    // reports per call as a RuntimeWarning (RVMC.py:177-180)
+    if (a.fail && threadIdx.x == 0 && (cnt_guard | cnt_bad)) {
+        if (cnt_guard) atomicAdd(a.fail + 2 * point, cnt_guard);
+        if (cnt_bad) atomicAdd(a.fail + 2 * point + 1, cnt_bad);
+    }
 }
 
 
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
     __shared__ int qn;
     __shared__ float wsum_s;
     __shared__ unsigned int cnt_guard, cnt_bad;
+    __shared__ unsigned int fail_k[2 * FBINS_MAX];       // per fraction: guard lanes, non-converged lanes
 
     const int64_t tile = blockIdx.x;
     const int64_t point = tile / a.tiles_per_point;
@@ -244,6 +252,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         uint32_t* dst = reinterpret_cast<uint32_t*>(&pt);
         for (int i = threadIdx.x; i < (int)(sizeof(FusedPoint) / 4); i += blockDim.x) dst[i] = src[i];
     }
+    if (threadIdx.x < 2 * FBINS_MAX) fail_k[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         qn = 0;
         cnt_guard = 0;
@@ -329,6 +338,16 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         rv[l] = orbit_rv_f32<ITERS, GUARD>(pt.pop, o, pt.kepler_iters, nullptr, g, b);
         my_guard += g;
         my_bad += b;
+        if (g | b) {
+            // (never with the reference's eccentricity bounds) the orbit counts for every fraction whose
+            // coin threshold makes this slot a binary
+            const uint32_t c = coin[l];
+            for (int k = 0; k < fa.n_fbins; ++k)
+                if (c < fa.thresh[k]) {
+                    if (g) atomicAdd(&fail_k[2 * k], 1u);
+                    if (b) atomicAdd(&fail_k[2 * k + 1], 1u);
+                }
+        }
     }
     if (my_guard) atomicAdd(&cnt_guard, my_guard);
     if (my_bad) atomicAdd(&cnt_bad, my_bad);
@@ -389,6 +408,8 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         if (cnt_guard) atomicAdd(a.counters + 1, (unsigned long long)cnt_guard);
         if (cnt_bad) atomicAdd(a.counters + 2, (unsigned long long)cnt_bad);
     }
+    if (a.fail && (cnt_guard | cnt_bad) && threadIdx.x < 2 * fa.n_fbins && fail_k[threadIdx.x])
+        atomicAdd(a.fail + 2 * point * fa.n_fbins + threadIdx.x, fail_k[threadIdx.x]);
 }
 
 // Per-slot dump of what the fused kernel computes (parity/debug entry): same device functions,
@@ -437,8 +458,8 @@ __global__ void fused_trace_kernel(FusedPoint pt, const float* __restrict__ meas
 // ---------------------------------------------------------------------------------------------
 // One block per point.  Exact order statistics by a most-significant-digit radix select on the
 // float bit patterns (sigma >= 0, so the unsigned order is the numeric order) in three passes of
-// 12 + 10 + 10 bits over the point's sigma array, which the fused kernel has just written and is L2
-// resident.  The ten ranks needed for the 5/16/50/84/95 percentiles (NumPy 'linear' rule: virtual
+// 12 + 10 + 10 bits over the point's sigma array (three streaming reads: a batch of rows is larger
+// than the L2, see point_stats_cluster_kernel for the single-read form).  The ten ranks needed for the 5/16/50/84/95 percentiles (NumPy 'linear' rule: virtual
 // index q/100*(n-1), neighbours floor and floor+1) are selected together:
 //   pass 0  one 4096-bin histogram of the top 12 bits (run-length cached per thread: neighbouring
 //           values share them) + the sum (fp64) and the maximum;
@@ -464,6 +485,7 @@ struct StatsArgs {
     int32_t hist_bins;         // row length of hist_out
     rvmc_point_stats* stats_out;
     uint32_t* hist_out;        // [n_points][hist_bins] or nullptr
+    const uint32_t* fail;      // [n_points][2] {guard lanes, non-converged lanes} of the producer, or nullptr
 };
 
 __device__ __forceinline__ double block_sum_f64(double x, double* scratch) {
@@ -712,8 +734,8 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) point_stats_kernel(StatsArgs
         st->mean = sum / (double)n;
         st->sigma_max = smax;
         st->n_hist_bins = (uint32_t)nb_mode;
-        st->n_guard = 0;
-        st->n_nonconverged = 0;
+        st->n_guard = a.fail ? a.fail[2 * blockIdx.x] : 0u;
+        st->n_nonconverged = a.fail ? a.fail[2 * blockIdx.x + 1] : 0u;
         st->reserved = 0;
         if (nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX) {
             st->mode = (double)mode_arg * a.bin + a.bin / 2.0;
@@ -790,7 +812,7 @@ static int fused_tile_shape(int S, TileShape* ts) {
 static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, int64_t n_points, const float* meas_err, int S, int weighted,
                         int ddof, uint64_t first_real, int64_t n_real, float* sigma_out, int64_t sigma_stride,
                         uint64_t* counters, bool iters1, bool guard, cudaStream_t stream,
-                        const uint64_t* common_seed = nullptr) {
+                        const uint64_t* common_seed = nullptr, uint32_t* fail = nullptr) {
     TileShape ts;
     int rc = fused_tile_shape(S, &ts);
     if (rc) return rc;
@@ -804,6 +826,7 @@ static int launch_fused(const FusedPoint* single, const FusedPoint* d_points, in
     a.meas_err = meas_err;
     a.sigma_out = sigma_out;
     a.counters = (unsigned long long*)counters;
+    a.fail = fail;
     a.first_real = first_real;
     a.n_real = n_real;
     a.sigma_stride = sigma_stride;
@@ -932,16 +955,21 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     const bool keyed = common_seed_of(host, &shared_seed);
     // stream-ordered scratch for the descriptors: no library-global state, so concurrent calls on
     // different streams do not interact
+    // [descriptors | per-point failure counters]
     void* ws = nullptr;
-    RVMC_CUDA(cudaMallocAsync(&ws, sizeof(FusedPoint) * (size_t)n_points, stream));
+    const size_t desc_bytes = sizeof(FusedPoint) * (size_t)n_points;
+    const size_t fail_bytes = 2 * sizeof(uint32_t) * (size_t)n_points;
+    RVMC_CUDA(cudaMallocAsync(&ws, desc_bytes + fail_bytes, stream));
     // the copy from pageable memory has been staged by the time the call returns; `host` may die
-    rc = cuda_status(cudaMemcpyAsync(ws, host.data(), sizeof(FusedPoint) * (size_t)n_points,
-                                     cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(points)");
+    rc = cuda_status(cudaMemcpyAsync(ws, host.data(), desc_bytes, cudaMemcpyHostToDevice, stream),
+                     "cudaMemcpyAsync(points)");
+    if (!rc) rc = cuda_status(cudaMemsetAsync((char*)ws + desc_bytes, 0, fail_bytes, stream), "cudaMemsetAsync");
     if (rc) {
         cudaFreeAsync(ws, stream);
         return rc;
     }
     const FusedPoint* d_points = (const FusedPoint*)ws;
+    uint32_t* d_fail = (uint32_t*)((char*)ws + desc_bytes);
 
     const int64_t tiles_per_point = (n_real + ts.R - 1) / ts.R;
     int64_t batch = rvmc_grid_scratch_slots(0) / 2;               // the scratch is used as two halves
@@ -967,7 +995,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         if (!sigma_out && nb >= 2) rc = cuda_status(cudaStreamWaitEvent(stream, ev_stats[half], 0), "cudaStreamWaitEvent");
         if (rc) break;
         rc = launch_fused(nullptr, d_points + p0, np, meas_err, sample_size, weighted, ddof, 0, n_real, sig, n_real,
-                          counters, iters1, guard, stream, keyed ? &shared_seed : nullptr);
+                          counters, iters1, guard, stream, keyed ? &shared_seed : nullptr, d_fail + 2 * p0);
         if (rc) break;
         rc = cuda_status(cudaEventRecord(ev_fused, stream), "cudaEventRecord");
         if (!rc) rc = cuda_status(cudaStreamWaitEvent(side, ev_fused, 0), "cudaStreamWaitEvent");
@@ -980,6 +1008,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         sa.hist_bins = hist_bins;
         sa.stats_out = stats_out + p0;
         sa.hist_out = hist_out ? hist_out + (size_t)p0 * hist_bins : nullptr;
+        sa.fail = d_fail + 2 * p0;
         point_stats_kernel<<<(unsigned int)np, STATS_THREADS, STATS_SMEM_BYTES, side>>>(sa);
         rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
         if (!rc) rc = cuda_status(cudaEventRecord(ev_stats[half], side), "cudaEventRecord");
@@ -1044,14 +1073,18 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
     const bool keyed = common_seed_of(host, &shared_seed);
     if (keyed) fa.base.key = philox_key(shared_seed);
     void* ws = nullptr;
-    RVMC_CUDA(cudaMallocAsync(&ws, sizeof(FusedPoint) * (size_t)n_points, stream));
-    rc = cuda_status(cudaMemcpyAsync(ws, host.data(), sizeof(FusedPoint) * (size_t)n_points, cudaMemcpyHostToDevice,
-                                     stream), "cudaMemcpyAsync(points)");
+    const size_t desc_bytes = sizeof(FusedPoint) * (size_t)n_points;
+    const size_t fail_bytes = 2 * sizeof(uint32_t) * (size_t)n_points * (size_t)n_fbins;
+    RVMC_CUDA(cudaMallocAsync(&ws, desc_bytes + fail_bytes, stream));
+    rc = cuda_status(cudaMemcpyAsync(ws, host.data(), desc_bytes, cudaMemcpyHostToDevice, stream),
+                     "cudaMemcpyAsync(points)");
+    if (!rc) rc = cuda_status(cudaMemsetAsync((char*)ws + desc_bytes, 0, fail_bytes, stream), "cudaMemsetAsync");
     if (rc) {
         cudaFreeAsync(ws, stream);
         return rc;
     }
     const FusedPoint* d_points = (const FusedPoint*)ws;
+    uint32_t* d_fail = (uint32_t*)((char*)ws + desc_bytes);
 
     const int S = sample_size;
     // Tile height: up to 3072 slots, and -- for the small clusters whose phase C runs one thread per
@@ -1109,6 +1142,7 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
         fa.base.meas_err = meas_err;
         fa.base.sigma_out = sig;
         fa.base.counters = (unsigned long long*)counters;
+        fa.base.fail = d_fail + 2 * p0 * n_fbins;
         fa.base.first_real = 0;
         fa.base.n_real = n_real;
         fa.base.sigma_stride = n_real;
@@ -1138,6 +1172,7 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
         sa.hist_bins = hist_bins;
         sa.stats_out = stats_out + p0 * n_fbins;
         sa.hist_out = hist_out ? hist_out + (size_t)p0 * n_fbins * hist_bins : nullptr;
+        sa.fail = d_fail + 2 * p0 * n_fbins;
         point_stats_kernel<<<(unsigned int)rows, STATS_THREADS, STATS_SMEM_BYTES, side>>>(sa);
         rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
         if (!rc) rc = cuda_status(cudaEventRecord(ev_stats[half], side), "cudaEventRecord");

@@ -87,10 +87,45 @@ def dist_info(group=None):
     return 0, 1
 
 
-def shard_indices(n_points, rank, world):
-    """Grid points dealt round-robin: rank r owns r, r+world, ... (cost varies smoothly along the
-    axes, so interleaving balances the ranks)."""
-    return np.arange(rank, n_points, world, dtype=np.int64)
+def shard_indices(n_points, rank, world, cost=None):
+    """Grid points owned by `rank` (int64, in the order the rank evaluates them).
+
+    `cost=None`: all points cost the same -- rank r owns r, r+world, ...
+    `cost` = per-point relative cost (one entry per point; the Monte-Carlo work of a point is
+    proportional to sample_size * fbin): the points are ordered by descending cost (ties by
+    grid index) and dealt round-robin in THAT order.  Every rank then holds the same number of points of
+    every cost level to within one, and the total cost of two ranks differs by less than the cost range
+    of a single point -- whatever the grid axes' lengths are.  (Dealing the C-order index round-robin is
+    balanced only while `world` does not divide the fastest axis: 16 binary fractions over 8 ranks gave
+    rank 7 the fractions {0.5, 1.0} and rank 0 {0.0625, 0.5625}, 1.5 : 0.6 in work.)
+    The owner of a point depends on (n_points, world, cost) only, so every rank derives the same deal."""
+    if cost is None:
+        return np.arange(rank, n_points, world, dtype=np.int64)
+    cost = np.asarray(cost, dtype=np.float64).ravel()
+    if cost.size != n_points:
+        raise ValueError("need one cost per grid point")
+    order = np.argsort(-cost, kind="stable")
+    return order[rank::world].astype(np.int64, copy=False)
+
+
+def shard_grid_indices(shape, cost_axis, axis_cost, rank, world):
+    """shard_indices for a Cartesian grid whose cost depends on ONE axis (the binary fraction): the same
+    deal, computed in O(points / world) without touching the other ranks' points.  `shape`: grid shape
+    (C order), `cost_axis`: index of the axis that sets the cost, `axis_cost`: cost of each value along it.
+    Returns this rank's flat C-order indices."""
+    shape = tuple(int(n) for n in shape)
+    n_points = int(np.prod(shape))
+    n_class = shape[cost_axis]
+    n_other = n_points // n_class
+    axis_cost = np.asarray(axis_cost, dtype=np.float64).ravel()
+    if axis_cost.size != n_class:
+        raise ValueError("need one cost per value of the cost axis")
+    classes = np.argsort(-axis_cost, kind="stable")            # cost levels, dearest first
+    pos = np.arange(rank, n_points, world, dtype=np.int64)      # positions of this rank in the dealt order
+    c = classes[pos // n_other]                                 # value index along the cost axis
+    j = pos % n_other                                           # rank among the points of that level (C order)
+    inner = int(np.prod(shape[cost_axis + 1:], dtype=np.int64))
+    return (j // inner) * (n_class * inner) + c * inner + (j % inner)
 
 
 def _records(byte_tensor):
@@ -101,26 +136,82 @@ def _records(byte_tensor):
     return host.numpy().view(STATS_DTYPE)
 
 
-def gather_point_stats(local_bytes, n_points, rank, world, group=None):
-    """All-gather of the per-point statistics.  `local_bytes`: uint8 tensor [n_local*80] (CPU for
-    gloo, CUDA for NCCL) holding this rank's rvmc_point_stats in shard order.  Returns a NumPy
-    structured array [n_points] in grid order on every rank."""
+def combine_point_stats(local_bytes, local, n_points, row_len, world, group=None):
+    """The per-point statistics of every rank -> one table in grid order on every rank.
+
+    `local_bytes`: uint8 tensor [n_local * row_len * 80] (CPU for gloo, CUDA for NCCL) with this rank's
+    rvmc_point_stats in the order of `local` (its grid indices).  Each rank scatters its records into a
+    zeroed [n_points, row_len] table ON ITS DEVICE and the tables are summed as 32-bit integers (one
+    all-reduce: every record has exactly one non-zero contributor, so the sum is exact and in grid order);
+    one device-to-host copy of the finished table follows.  Host work per rank is O(points / world): no
+    per-rank Python loop, no fancy indexing of 80-byte records (7 ms for 65 536 of them)."""
     import torch
-    item = STATS_DTYPE.itemsize
-    if world == 1:
-        return _records(local_bytes)
-    import torch.distributed as dist
-    n_max = (n_points + world - 1) // world
-    pad = torch.zeros(n_max * item, dtype=torch.uint8, device=local_bytes.device)
-    pad[:local_bytes.numel()] = local_bytes
-    out = torch.empty(world * n_max * item, dtype=torch.uint8, device=local_bytes.device)
-    dist.all_gather_into_tensor(out, pad, group=group)
-    raw = _records(out).reshape(world, n_max)
-    res = np.empty(n_points, dtype=STATS_DTYPE)
-    for r in range(world):
-        idx = shard_indices(n_points, r, world)
-        res[idx] = raw[r, :len(idx)]
-    return res
+    words = STATS_DTYPE.itemsize * row_len // 4
+    nl = len(local)
+    if world == 1 and nl == n_points and (nl == 0 or (local[0] == 0 and local[-1] == nl - 1 and
+                                                      np.all(np.diff(local) == 1))):
+        return _records(local_bytes).reshape(n_points, row_len)
+    dev = local_bytes.device
+    table = torch.zeros((n_points, words), dtype=torch.int32, device=dev)
+    if nl:
+        idx = torch.from_numpy(np.ascontiguousarray(local, dtype=np.int64)).to(dev)
+        table.index_copy_(0, idx, local_bytes[:nl * words * 4].view(torch.int32).view(nl, words))
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(table, group=group)
+    return _records(table.view(torch.uint8).view(-1)).reshape(n_points, row_len)
+
+
+def gather_point_stats(local_bytes, n_points, rank, world, group=None, local=None):
+    """combine_point_stats for one record per point; `local` defaults to the uniform-cost deal."""
+    if local is None:
+        local = shard_indices(n_points, rank, world)
+    return combine_point_stats(local_bytes, local, n_points, 1, world, group).reshape(n_points)
+
+
+def gather_point_stats_rows(local_bytes, n_points, row_len, rank, world, group=None, local=None):
+    """combine_point_stats for `row_len` consecutive records per point -> [n_points, row_len]."""
+    if local is None:
+        local = shard_indices(n_points, rank, world)
+    return combine_point_stats(local_bytes, local, n_points, row_len, world, group)
+
+
+_scratch_cache = {}
+
+
+def _scratch(lib, dev, ns):
+    """The sigma_1D scratch of rvmc_grid_run* (scratch_slots x number_of_samples floats, ~0.5 GB at 10^5
+    realizations), kept per (device, stream) between calls: a grid fit calls run_points many times and
+    every call would otherwise allocate it afresh.  Calls on one stream are ordered, so reuse is safe."""
+    t = dv.torch()
+    key = (dev.index, t.cuda.current_stream(dev).cuda_stream)
+    need = int(lib.rvmc_grid_scratch_slots(dev.index)) * int(ns)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < need:
+        buf = dv.empty((need,), "float32", dev)
+        _scratch_cache[key] = buf
+    return buf
+
+
+def point_cost(pops, sample_size):
+    """Relative Monte-Carlo cost of grid points: the expected number of binary orbits per realization,
+    sample_size * fbin (phases A and C of the fused kernel cost the same for every point)."""
+    return float(sample_size) * np.asarray(pops["fbin"], dtype=np.float64)
+
+
+def _check_indices(pops):
+    for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
+        if np.any(pops[f] == -1.0):
+            raise ZeroDivisionError("float division by zero")          # RVMC.py:112
+
+
+def _warn_nonconverged(stats):
+    bad = int(stats["n_nonconverged"].sum())
+    if bad:
+        import warnings
+        # scipy.optimize.newton's RuntimeWarning for array input (RVMC.py:177-180)
+        warnings.warn("some failed to converge after 50 iterations (%d orbits in %d grid points)"
+                      % (bad, int(np.count_nonzero(stats["n_nonconverged"]))), RuntimeWarning)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -156,43 +247,58 @@ def point_seeds(seed, n_points, common_random_numbers=False):
     return z
 
 
-def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**5, bin=0.5, ddof=0,
-               weighted=False, keep_sigma=False, keep_hist=False, hist_bins=2048, device=None, group=None,
-               distributed=True):
-    """Evaluates grid points (list of PopParams + list of seeds) on the GPU(s).
-
-    Returns a dict: 'stats' (structured array [n_points], every rank), 'sigma' (float32
-    [n_points, number_of_samples] or None; local points only are filled when sharded), 'hist'
-    (uint32 [n_points, hist_bins] or None, same remark), 'counters' (binary RVs, guard,
-    non-converged of THIS rank), 'local' (indices this rank computed)."""
+def _local_share(pops, seeds, sample_size, rank, world, local, n_points):
+    """(records of this rank's points, their grid indices, n_points).  `pops` is the FULL list / record
+    array unless `local` (grid indices of the records in `pops`, which is then the rank's share already)
+    and `n_points` are given -- the form grid_search uses so that no rank ever builds the whole grid."""
+    if local is not None:
+        if not (isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE) or len(pops) != len(local):
+            raise ValueError("with `local`, pops must be this rank's POINT_DTYPE records")
+        _check_indices(pops)
+        return np.ascontiguousarray(pops), np.asarray(local, dtype=np.int64), int(n_points)
+    if not (isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE):
+        pops = _as_points(pops, seeds)
+        seeds = None
     n_points = len(pops)
     if seeds is not None and len(seeds) != n_points:
         raise ValueError("need one seed per grid point")
+    _check_indices(pops)                 # every rank checks the list it was handed, so all ranks raise together
+    cost = point_cost(pops, sample_size) if world > 1 else None
+    if cost is not None and np.all(cost == cost[0]):
+        cost = None
+    local = shard_indices(n_points, rank, world, cost)
+    pts = np.ascontiguousarray(pops[local])
+    if seeds is not None:
+        pts["seed"] = np.asarray(seeds, dtype=np.uint64)[local]
+    return pts, local, n_points
+
+
+def _check_errors(measured_errors, sample_size):
     err = np.ascontiguousarray(measured_errors, dtype=np.float32)
     if err.ndim != 1 or err.size != int(sample_size):
         raise ValueError("measured_errors must have sample_size = %d entries (got shape %s)"
                          % (int(sample_size), err.shape))
+    return err
+
+
+def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**5, bin=0.5, ddof=0,
+               weighted=False, keep_sigma=False, keep_hist=False, hist_bins=2048, device=None, group=None,
+               distributed=True, local=None, n_points=None):
+    """Evaluates grid points (list of PopParams + list of seeds, or POINT_DTYPE records) on the GPU(s).
+
+    With torch.distributed initialised the points are dealt to the ranks by cost (shard_indices:
+    cost = sample_size * fbin), each point wholly on one GPU; pass `local` + `n_points` when `pops` already
+    is this rank's share.  Returns a dict: 'stats' (structured array [n_points] in grid order, every
+    rank), 'sigma' (float32 [n_local, number_of_samples] or None, rows in the order of 'local'), 'hist'
+    (uint32 [n_local, hist_bins] or None, same order), 'counters' (binary RVs, guard, non-converged of
+    THIS rank), 'local' (grid indices this rank computed)."""
+    err = _check_errors(measured_errors, sample_size)
     rank, world = dist_info(group) if distributed else (0, 1)
-    local = shard_indices(n_points, rank, world)
+    pts_np, local, n_points = _local_share(pops, seeds, sample_size, rank, world, local, n_points)
     nl = len(local)
-    if isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE:
-        # every rank checks ALL points (so that all ranks raise together) but copies only its share
-        for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
-            if np.any(pops[f] == -1.0):
-                raise ZeroDivisionError("float division by zero")          # RVMC.py:112
-        pts_np = np.ascontiguousarray(pops[rank::world])
-        if seeds is not None:
-            pts_np["seed"] = np.asarray(seeds, dtype=np.uint64)[rank::world]
-    else:
-        all_pts = _as_points(pops, seeds)
-        for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
-            if np.any(all_pts[f] == -1.0):
-                raise ZeroDivisionError("float division by zero")
-        pts_np = np.ascontiguousarray(all_pts[rank::world])
     if not nl:
         pts_np = np.zeros(1, dtype=POINT_DTYPE)
     dev = dv.resolve_device(device)
-    t = dv.torch()
     ns = int(number_of_samples)
     pts = pts_np.ctypes.data_as(C.POINTER(_abi.GridPoint))
     stats_d = dv.zeros((max(nl, 1) * STATS_DTYPE.itemsize,), "uint8", dev)
@@ -202,53 +308,47 @@ def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**
     hist_d = dv.zeros((nl, int(hist_bins)), "int32", dev) if keep_hist and nl else None
     with dv.DeviceGuard(dev):
         lib = _abi.lib()
-        scratch = None
-        if sigma_d is None and nl:
-            scratch = dv.empty((lib.rvmc_grid_scratch_slots(dev.index), ns), "float32", dev)
+        scratch = _scratch(lib, dev, ns) if sigma_d is None and nl else None
         _abi.check(lib.rvmc_grid_run(pts, nl, dv.ptr(errd), int(sample_size), int(bool(weighted)), int(ddof), ns,
                                      float(bin), int(hist_bins), dv.ptr(stats_d), dv.ptr(sigma_d), dv.ptr(hist_d),
                                      dv.ptr(scratch), dv.ptr(counters), dv.stream_ptr(dev)))
-        stats = gather_point_stats(stats_d[:nl * STATS_DTYPE.itemsize], n_points, rank, world, group)
+        stats = combine_point_stats(stats_d, local, n_points, 1, world, group).reshape(n_points)
     out = dict(stats=stats, local=local, counters=dv.to_host(counters), sigma=None, hist=None)
     if sigma_d is not None:
         out["sigma"] = dv.to_host(sigma_d)
     if hist_d is not None:
         out["hist"] = dv.to_host(hist_d).view(np.uint32)
+    _finish(stats)
+    return out
+
+
+def _finish(stats):
     bad = int(stats["reserved"].sum())
     if bad:
         raise NotImplementedError("%d grid points have sigma_1D histograms wider than the %d bins the statistics "
                                   "kernel holds; use a larger `bin`" % (bad, 4096))
-    return out
+    _warn_nonconverged(stats)
 
 
 def run_points_fbins(pops, seeds, fbins, measured_errors, sample_size, number_of_samples=10**5, bin=0.5, ddof=0,
                      weighted=False, keep_sigma=False, keep_hist=False, hist_bins=2048, device=None, group=None,
-                     distributed=True):
+                     distributed=True, local=None, n_points=None):
     """Like run_points for the Cartesian product (points x fbins) with each point's seed shared along
     the f_bin axis: rvmc_grid_run_fbins samples and solves every star slot once and reduces once per
     binary fraction -- bit-identical to run_points on the expanded list, at about the cost of the
-    largest fraction alone.  Returns 'stats' [n_points, n_fbins] (every rank), 'sigma'
-    [n_local, n_fbins, n_real] or None, 'hist' [n_local, n_fbins, hist_bins] or None, 'counters', 'local'."""
-    if not (isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE):
-        pops = _as_points(pops, seeds)
-        seeds = None
-    n_points = len(pops)
+    largest fraction alone (so every point costs the same and the deal is plain round-robin).  Returns
+    'stats' [n_points, n_fbins] (every rank), 'sigma' [n_local, n_fbins, n_real] or None, 'hist'
+    [n_local, n_fbins, hist_bins] or None, 'counters', 'local'."""
     fb = np.ascontiguousarray(fbins, dtype=np.float64).ravel()
     if fb.size < 1:
         raise ValueError("need at least one binary fraction")
-    err = np.ascontiguousarray(measured_errors, dtype=np.float32)
-    if err.ndim != 1 or err.size != int(sample_size):
-        raise ValueError("measured_errors must have sample_size = %d entries (got shape %s)"
-                         % (int(sample_size), err.shape))
-    for f in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power"):
-        if np.any(pops[f] == -1.0):
-            raise ZeroDivisionError("float division by zero")          # RVMC.py:112
+    err = _check_errors(measured_errors, sample_size)
     rank, world = dist_info(group) if distributed else (0, 1)
-    local = shard_indices(n_points, rank, world)
+    if local is None and isinstance(pops, np.ndarray) and pops.dtype == POINT_DTYPE:
+        pops = pops.copy()
+        pops["fbin"] = 1.0               # unused along the fused axis: every point costs the same
+    pts_np, local, n_points = _local_share(pops, seeds, sample_size, rank, world, local, n_points)
     nl = len(local)
-    pts_np = np.ascontiguousarray(pops[rank::world])
-    if seeds is not None:
-        pts_np["seed"] = np.asarray(seeds, dtype=np.uint64)[rank::world]
     if not nl:
         pts_np = np.zeros(1, dtype=POINT_DTYPE)
     dev = dv.resolve_device(device)
@@ -268,46 +368,23 @@ def run_points_fbins(pops, seeds, fbins, measured_errors, sample_size, number_of
             stats_d = dv.zeros((max(nl, 1) * nf * item,), "uint8", dev)
             sigma_d = dv.empty((nl, nf, ns), "float32", dev) if keep_sigma and nl else None
             hist_d = dv.zeros((nl, nf, int(hist_bins)), "int32", dev) if keep_hist and nl else None
-            scratch = None
-            if sigma_d is None and nl:
-                scratch = dv.empty((lib.rvmc_grid_scratch_slots(dev.index), ns), "float32", dev)
+            scratch = _scratch(lib, dev, ns) if sigma_d is None and nl else None
             _abi.check(lib.rvmc_grid_run_fbins(pts, nl, sub.ctypes.data_as(C.POINTER(C.c_double)), nf, dv.ptr(errd),
                                                int(sample_size), int(bool(weighted)), int(ddof), ns, float(bin),
                                                int(hist_bins), dv.ptr(stats_d), dv.ptr(sigma_d), dv.ptr(hist_d),
                                                dv.ptr(scratch),
                                                dv.ptr(counters), dv.stream_ptr(dev)))
-            # gather rows of nf records per point
-            flat = gather_point_stats_rows(stats_d[:nl * nf * item], n_points, nf, rank, world, group)
-            stats_all[:, k0:k0 + nf] = flat
+            part = combine_point_stats(stats_d, local, n_points, nf, world, group)
+            if nf == fb.size:
+                stats_all = part
+            else:
+                stats_all[:, k0:k0 + nf] = part
             if sigma_d is not None:
                 sigma_all[:, k0:k0 + nf] = dv.to_host(sigma_d)
             if hist_d is not None:
                 hist_all[:, k0:k0 + nf] = dv.to_host(hist_d).view(np.uint32)
-    bad = int(stats_all["reserved"].sum())
-    if bad:
-        raise NotImplementedError("%d grid points have sigma_1D histograms wider than the %d bins the statistics "
-                                  "kernel holds; use a larger `bin`" % (bad, 4096))
+    _finish(stats_all)
     return dict(stats=stats_all, local=local, counters=dv.to_host(counters), sigma=sigma_all, hist=hist_all)
-
-
-def gather_point_stats_rows(local_bytes, n_points, row_len, rank, world, group=None):
-    """gather_point_stats for `row_len` consecutive records per point -> [n_points, row_len]."""
-    import torch
-    item = STATS_DTYPE.itemsize * row_len
-    if world == 1:
-        return _records(local_bytes).reshape(n_points, row_len)
-    import torch.distributed as dist
-    n_max = (n_points + world - 1) // world
-    pad = torch.zeros(n_max * item, dtype=torch.uint8, device=local_bytes.device)
-    pad[:local_bytes.numel()] = local_bytes
-    out = torch.empty(world * n_max * item, dtype=torch.uint8, device=local_bytes.device)
-    dist.all_gather_into_tensor(out, pad, group=group)
-    raw = _records(out).reshape(world, n_max, row_len)
-    res = np.empty((n_points, row_len), dtype=STATS_DTYPE)
-    for r in range(world):
-        idx = shard_indices(n_points, r, world)
-        res[idx] = raw[r, :len(idx)]
-    return res
 
 
 def _pop_for(min_mass, max_mass, fbin, min_period, max_period, sigma_dyn, **extra):
@@ -576,40 +653,53 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
     vals = [np.asarray(axes[k], dtype=np.float64) for k in names]
     shape = tuple(len(v) for v in vals)
     fused_axis = names.index("fbin") if (share_fbin_draws and "fbin" in names) else None
+    rank, world = dist_info(group) if distributed else (0, 1)
+    # indices of -1 raise before any rank builds anything (RVMC.py:112); O(sum of the axis lengths)
+    for k, v in list(zip(names, vals)) + list((base or {}).items()):
+        if k in ("mass_power", "period_pi", "mass_ratio_kappa", "e_power") and np.any(np.asarray(v) == -1.0):
+            raise ZeroDivisionError("float division by zero")
+    o_names = [k for k in names if fused_axis is None or k != "fbin"]
+    o_vals = [v for k, v in zip(names, vals) if fused_axis is None or k != "fbin"]
+    o_shape = tuple(len(v) for v in o_vals)
+    n_points = int(np.prod(o_shape)) if o_shape else 1
+    # this rank's share of the points, by cost: only an un-fused f_bin axis makes points differ in cost
+    # (cost = sample_size * fbin); the deal is computed without enumerating the other ranks' points
+    if fused_axis is None and "fbin" in o_names and world > 1:
+        local = shard_grid_indices(o_shape, o_names.index("fbin"), o_vals[o_names.index("fbin")], rank, world)
+    else:
+        local = shard_indices(n_points, rank, world)
+    # ... and only this rank's records are ever built: column k of point i is axis value multi_index_k(i)
+    cols = dict(base or {})
+    if o_shape:
+        for k, v, mi in zip(o_names, o_vals, np.unravel_index(local, o_shape)):
+            cols[k] = v[mi]
+    pops = points_array(len(local), **cols)
+    pops["seed"] = np.uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)
+    pops["substream"] = 0 if common_random_numbers else local.astype(np.uint32)     # == with_streams on the full grid
     if fused_axis is None:
-        mesh = np.meshgrid(*vals, indexing="ij")
-        cols = dict(base or {})
-        cols.update({k: m.ravel() for k, m in zip(names, mesh)})
-        pops = points_array(int(np.prod(shape)), **cols)
-        res = run_points(with_streams(pops, seed, common_random_numbers), None,
-                         _errs(measured_errors, sample_size), sample_size, number_of_samples, bin=bin, ddof=ddof,
-                         device=device, group=group, distributed=distributed)
+        res = run_points(pops, None, _errs(measured_errors, sample_size), sample_size, number_of_samples, bin=bin,
+                         ddof=ddof, device=device, group=group, distributed=distributed, local=local,
+                         n_points=n_points)
         stats = res["stats"].reshape(shape)
     else:
         # the f_bin axis shares each point's draws and is evaluated in one pass (rvmc_grid_run_fbins)
-        o_names = [k for k in names if k != "fbin"]
-        o_vals = [v for k, v in zip(names, vals) if k != "fbin"]
-        o_shape = tuple(len(v) for v in o_vals)
-        n_other = int(np.prod(o_shape)) if o_shape else 1
-        cols = dict(base or {})
-        if o_vals:
-            mesh = np.meshgrid(*o_vals, indexing="ij")
-            cols.update({k: m.ravel() for k, m in zip(o_names, mesh)})
-        pops = points_array(n_other, **cols)
-        res = run_points_fbins(with_streams(pops, seed, common_random_numbers), None, vals[fused_axis],
-                               _errs(measured_errors, sample_size), sample_size, number_of_samples, bin=bin,
-                               ddof=ddof, device=device, group=group, distributed=distributed)
+        res = run_points_fbins(pops, None, vals[fused_axis], _errs(measured_errors, sample_size), sample_size,
+                               number_of_samples, bin=bin, ddof=ddof, device=device, group=group,
+                               distributed=distributed, local=local, n_points=n_points)
         stats = np.moveaxis(res["stats"].reshape(o_shape + (shape[fused_axis],)), -1, fused_axis)
-    out = dict(axes=dict(zip(names, vals)), shape=shape, stats=np.ascontiguousarray(stats), counters=res["counters"],
+    out = dict(axes=dict(zip(names, vals)), shape=shape, stats=stats, counters=res["counters"],
                n_local=len(res["local"]), fbin_axis_fused=fused_axis is not None)
     if observed_sigma is not None:
-        central = out["stats"]["mode" if usemode else "median"].ravel()
+        # findBestDistributions.py:138-158: first strict minimum below the initial distance of 100, in C
+        # order; the strict `<` never selects a NaN (an all-zero sigma_1D distribution has no mode), so
+        # NaNs are masked out rather than left to np.argmin, which would return the first of them
+        central = out["stats"]["mode" if usemode else "median"]
         d = np.abs(central - observed_sigma)
+        ok = d < 100                                   # False for NaN
         best, idx = 100.0, 0
-        hits = np.nonzero(d < 100)[0]
-        if len(hits):
-            idx = int(np.argmin(d))            # np.argmin returns the first minimum, like the strict `<` loop
-            best = float(d[idx])
+        if ok.any():
+            idx = int(np.argmin(np.where(ok, d, np.inf)))          # first minimum in C order
+            best = float(d.flat[idx])
         out["best_index"] = tuple(int(v) for v in np.unravel_index(idx, shape))
         out["best_params"] = {k: float(v[j]) for k, v, j in zip(names, vals, out["best_index"])}
         out["best_distance"] = best

@@ -197,6 +197,37 @@ def test_grid_search_recovers_known_parameters():
     assert np.all(np.diff(med[:, 1, 3]) < 0) and np.all(np.diff(med[2, 1, :]) > 0)
 
 
+def test_grid_per_point_failure_counters_and_best_fit_ignores_nan():
+    """rvmc_point_stats.n_guard / n_nonconverged are filled per point by the producer kernels (what
+    scipy.optimize.newton reports per call, RVMC.py:177-180): with eccentricities up to 0.999 the fp64
+    guard engages, more often the more binaries a point has; the per-point counts add up to the call's
+    counters, along the fused f_bin axis too.  An all-zero sigma_1D point (mode NaN) never wins the best
+    fit (np.argmin returned the first NaN)."""
+    pops = [_abi.PopParams.defaults(e_max_long=0.999, fbin=f) for f in (0.2, 0.9)] + [_abi.PopParams.defaults()]
+    res = grid.run_points(pops, [3, 4, 5], M17, 12, 20000, distributed=False)
+    st = res["stats"]
+    assert st["n_guard"][0] > 0 and st["n_guard"][1] > 2 * st["n_guard"][0] and st["n_guard"][2] == 0
+    assert int(st["n_guard"].sum()) == int(res["counters"][1])
+    assert int(st["n_nonconverged"].sum()) == int(res["counters"][2]) == 0
+    fb = np.array([0.2, 1.0, 0.6])
+    rf = grid.run_points_fbins(pops[:1], [3], fb, M17, 12, 20000, distributed=False)
+    ng = rf["stats"]["n_guard"][0]
+    assert ng[1] == int(rf["counters"][1]) and ng[0] < ng[2] < ng[1] and ng[0] > 0
+    # bit-identity with the pointwise evaluation extends to the counters
+    exp = [_abi.PopParams.defaults(e_max_long=0.999, fbin=float(f)) for f in fb]
+    rp = grid.run_points(exp, [3, 3, 3], M17, 12, 20000, distributed=False)
+    np.testing.assert_array_equal(rp["stats"]["n_guard"], ng)
+    np.testing.assert_array_equal(rp["stats"]["median"], rf["stats"]["median"][0])
+    # NaN statistics are skipped by the best-fit rule (first strict minimum, findBestDistributions.py:138-158)
+    axes = dict(sigma_dyn=np.array([0.0, 2.0]), fbin=np.array([0.0, 0.5]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = grid.grid_search(axes, measured_errors=np.zeros(12), number_of_samples=2000, seed=3, observed_sigma=3.0,
+                             usemode=True, share_fbin_draws=False)
+    assert np.isnan(r["stats"]["mode"][0, 0])                 # sigma_dyn = 0, no binaries, no errors: all zeros
+    assert r["best_index"] != (0, 0) and np.isfinite(r["best_distance"])
+
+
 # ---- drop-in classes --------------------------------------------------------------------------------
 def test_rvmc_class_walkthrough_like_the_example_script():
     """RVMC_example.py:6-37 on the GPU."""
