@@ -253,6 +253,9 @@ RVMC_API int rvmc_unpack_bits_host(const uint32_t* bits_host, int64_t bits_strid
                           int64_t n_cols, uint8_t* out_host, int64_t out_stride, int n_threads);
 RVMC_API int rvmc_count_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, int64_t n_rows,
                          int64_t n_cols, int64_t* counts_host, int n_threads);
+/* memcpy with the same thread pool: moves a pinned staging block into pageable memory at DMA speed
+ * (results too large to pin are staged through two fixed pinned buffers, rvmc_b200/_device.py). */
+RVMC_API int rvmc_copy_host(void* dst_host, const void* src_host, int64_t nbytes, int n_threads);
 
 /* Materialised per-binary attribute arrays of BiasCorr (RVMC_bias_corr.py:175-243) for the
  * same (seed, star, sample) indexing as rvmc_biascorr_fused; fp64, layout [nstars][n_samples]. */

@@ -100,6 +100,7 @@ SIGNATURES = {
                                         _F, _F, _U64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),
     "rvmc_unpack_bits_host": (_I, [_VP, _I64, _I64, _I64, _VP, _I64, _I]),
     "rvmc_count_bits_host": (_I, [_VP, _I64, _I64, _I64, _VP, _I]),
+    "rvmc_copy_host": (_I, [_VP, _VP, _I64, _I]),
     "rvmc_biascorr_sample": (_I, [C.POINTER(PopParams), _U64, _I, _I, _VP, _VP, _U64, _I64, _U32, OrbitSoA, _VP]),
     "rvmc_kepler_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "rvmc_rv_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

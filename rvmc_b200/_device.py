@@ -73,7 +73,7 @@ def to_device(array, dtype, device):
 # NumPy array keeps it alive; it goes back to the cache when the array is collected).  Anything larger
 # is staged through two fixed pinned buffers into ordinary pageable memory, so reading a multi-GB
 # attribute array cannot grow the locked memory of the process.
-PIN_DIRECT_MAX = 256 << 20
+PIN_DIRECT_MAX = 512 << 20
 PIN_STAGE_BYTES = 32 << 20
 _stage = {}
 
@@ -105,6 +105,7 @@ def to_host(tensor):
     src = tensor.view(-1).view(t.uint8)
     dst = out.view(-1).view(t.uint8)
     bufs, evs = _stage_buffers(tensor.device)
+    lib, threads = _abi.lib(), host_threads()
     n_chunks = (nbytes + PIN_STAGE_BYTES - 1) // PIN_STAGE_BYTES
     for k in range(n_chunks + 1):
         if k < n_chunks:                                     # start the copy of chunk k ...
@@ -114,7 +115,7 @@ def to_host(tensor):
         if k >= 1:                                           # ... while chunk k-1 moves to its final place
             lo, hi = (k - 1) * PIN_STAGE_BYTES, min(nbytes, k * PIN_STAGE_BYTES)
             evs[(k - 1) & 1].synchronize()
-            dst[lo:hi].copy_(bufs[(k - 1) & 1][:hi - lo])
+            _abi.check(lib.rvmc_copy_host(dst.data_ptr() + lo, bufs[(k - 1) & 1].data_ptr(), hi - lo, threads))
     return out.numpy()
 
 

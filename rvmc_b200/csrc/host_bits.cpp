@@ -220,9 +220,39 @@ void count_task(void* ctx, int64_t row) {
     j.counts[row] = n;
 }
 
+struct CopyJob {
+    uint8_t* dst;
+    const uint8_t* src;
+    int64_t nbytes, seg;
+};
+
+void copy_task(void* ctx, int64_t task) {
+    const CopyJob& j = *static_cast<const CopyJob*>(ctx);
+    const int64_t lo = task * j.seg;
+    const int64_t n = (j.nbytes - lo < j.seg) ? j.nbytes - lo : j.seg;
+    memcpy(j.dst + lo, j.src + lo, (size_t)n);
+}
+
 }  // namespace
 
 extern "C" {
+
+int rvmc_copy_host(void* dst_host, const void* src_host, int64_t nbytes, int n_threads) {
+    if (nbytes < 0 || (nbytes > 0 && (!dst_host || !src_host))) {
+        rvmc::set_error("rvmc_copy_host: bad arguments");
+        return RVMC_ERR_INVALID;
+    }
+    if (nbytes == 0) return RVMC_OK;
+    CopyJob j;
+    j.dst = static_cast<uint8_t*>(dst_host);
+    j.src = static_cast<const uint8_t*>(src_host);
+    j.nbytes = nbytes;
+    j.seg = 1 << 20;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    pool().run((nbytes + j.seg - 1) / j.seg, n_threads, copy_task, &j);
+    return RVMC_OK;
+}
 
 int rvmc_unpack_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, int64_t n_rows, int64_t n_cols,
                           uint8_t* out_host, int64_t out_stride, int n_threads) {

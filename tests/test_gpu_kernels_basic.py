@@ -168,3 +168,17 @@ def test_error_conventions():
     assert rc == _abi.RVMC_ERR_INVALID and b"number of stars" in g.lib().rvmc_last_error()
     # empty input is fine
     g.ok(g.lib().rvmc_sample_orbits(C.byref(_abi.PopParams.defaults()), 1, 0, 0, 0, dv.soa(), None, g.stream()))
+
+
+def test_to_host_staged_path_equals_the_direct_copy(monkeypatch):
+    """Results above PIN_DIRECT_MAX are staged through two fixed pinned buffers into pageable memory
+    (reading a multi-GB attribute must not grow the locked memory of the process)."""
+    import torch
+    x = torch.arange(3_000_017, dtype=torch.float32, device=g.dev()).reshape(7, -1) * 0.5
+    want = x.cpu().numpy()
+    monkeypatch.setattr(dv, "PIN_DIRECT_MAX", 1 << 20)
+    monkeypatch.setattr(dv, "PIN_STAGE_BYTES", (1 << 20) + 4096)
+    monkeypatch.setattr(dv, "_stage", {})
+    got = dv.to_host(x)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    np.testing.assert_array_equal(got, want)

@@ -36,27 +36,38 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     dt = time.perf_counter() - t0
+    # independent draws per cell: the cost-aware deal (every rank gets every f_bin level)
+    ri = grid.grid_search(axes, number_of_samples=n_real, seed=11, observed_sigma=25.0, share_fbin_draws=False)
     cnt = torch.from_numpy(r["counters"].astype(np.int64)).to(dev)
     dist.all_reduce(cnt)
+    cost = torch.tensor([float(ri["counters"][0])], device=dev, dtype=torch.float64)
+    costs = [torch.zeros_like(cost) for _ in range(world)]
+    dist.all_gather(costs, cost)
     ok = True
     if rank == 0:
         single = grid.grid_search(axes, number_of_samples=n_real, seed=11, observed_sigma=25.0, distributed=False)
         same = all(np.array_equal(single["stats"][k], r["stats"][k]) for k in grid.STATS_DTYPE.names)
-        # and the f_bin-fused pass against plain point-by-point evaluation with the same seeds
-        plain = grid.grid_search(axes, number_of_samples=n_real, seed=11, share_fbin_draws=False, distributed=False)
+        # and the f_bin-fused pass against plain point-by-point evaluation with the same seed and substreams
+        plain = grid.grid_search(axes, number_of_samples=n_real, seed=11, observed_sigma=25.0, share_fbin_draws=False,
+                                 distributed=False)
+        same_indep = all(np.array_equal(plain["stats"][k], ri["stats"][k]) for k in grid.STATS_DTYPE.names) and \
+            plain["best_index"] == ri["best_index"]
         n_other = len(axes["period_pi"]) * len(axes["mass_ratio_kappa"])
-        seeds = np.repeat(grid.point_seeds(11, n_other), len(axes["fbin"]))
+        nf = len(axes["fbin"])
         mesh = np.meshgrid(*axes.values(), indexing="ij")
-        expanded = grid.run_points(grid.points_array(seeds.size, **{k: m.ravel() for k, m in zip(axes, mesh)}), seeds,
-                                   grid.M17_ERRORS, 12, n_real, distributed=False)
+        pts = grid.points_array(n_other * nf, **{k: m.ravel() for k, m in zip(axes, mesh)})
+        pts["seed"] = 11
+        pts["substream"] = np.repeat(np.arange(n_other, dtype=np.uint32), nf)     # the fused axis shares a substream
+        expanded = grid.run_points(pts, None, grid.M17_ERRORS, 12, n_real, distributed=False)
         same = same and all(np.array_equal(expanded["stats"][k], r["stats"][k].ravel()) for k in
                             ("median", "mean", "mode", "p05", "p95", "sigma_max"))
-        assert plain["stats"].shape == r["stats"].shape
-        ok = ok and same and int(cnt[0]) == int(single["counters"][0])
+        c = np.array([float(x.item()) for x in costs])
+        ok = ok and same and same_indep and int(cnt[0]) == int(single["counters"][0])
         print(json.dumps({"check": "grid sharded == single GPU", "world": world, "points": int(np.prod(r["shape"])),
-                          "identical": bool(same), "binary_rvs_all_ranks": int(cnt[0]),
-                          "binary_rvs_single": int(single["counters"][0]), "seconds_sharded": dt,
-                          "best_index": r["best_index"], "best_params": r["best_params"]}))
+                          "identical_fused_fbin_axis": bool(same), "identical_independent_cells": bool(same_indep),
+                          "binary_rvs_all_ranks": int(cnt[0]), "binary_rvs_single": int(single["counters"][0]),
+                          "seconds_sharded": dt, "best_index": r["best_index"], "best_params": r["best_params"],
+                          "independent_cells_binary_rvs_per_rank_spread": float((c.max() - c.min()) / c.mean())}))
     # multi-epoch: ranks take disjoint sample ranges; rank 0 recomputes the union on one GPU
     lib = _abi.lib()
     p = _abi.PopParams.defaults()
