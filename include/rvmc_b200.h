@@ -216,8 +216,8 @@ RVMC_API int rvmc_fused_trace(const rvmc_pop_params* p, uint64_t seed, const flo
  * quirk_phase != 0 reproduces RVMC_bias_corr.py:357.
  * Outputs (each may be NULL): delta_rv float32[nstars*n_samples] (:422), detected
  * uint8[nstars*n_samples] (:451-476), rv_out float32[nstars*max_epochs*n_samples] (the noisy
- * radial_velocities, :419-421), counters uint64[4] = {binary-epoch RVs, detected, guard,
- * non-converged} (accumulated), det_per_star uint32[nstars] (accumulated). */
+ * radial_velocities, :419-421), counters uint64[4] = {binary-epoch RVs, detected binaries, fp64-guard
+ * epochs, binaries with a Kepler residual above 1e-5 at any epoch} (accumulated), det_per_star uint32[nstars] (accumulated). */
 RVMC_API int rvmc_biascorr_fused(const rvmc_pop_params* p, uint64_t seed, uint64_t noise_seed, int first_star,
                         int nstars, int max_epochs,
                         const int32_t* n_epochs, const double* t_obs, const float* rv_err,

@@ -24,6 +24,7 @@ import numpy as np
 
 from . import _abi
 from . import _device as dv
+from ._trace import span
 from .rvmc import _check_powers
 
 _ORBIT = ("primary_mass", "period", "time", "mass_ratio", "eccentricity", "inclination", "orbit_rotation")
@@ -488,14 +489,14 @@ class BiasCorr(dv.LazyArrays):
         per_star = dv.zeros((max(nstars, 1),), "int32", dev)
         # large problems go out as a few launches over star ranges (sample ranges when there are only
         # a few stars): the copy of one range's results to the host (get_detected_binaries) then overlaps
-        # the compute of the next ranges.  The ranges taper (each about 0.7 of the previous one) so that
-        # the last copy, which nothing overlaps, is small; everything launch-invariant is prepared once.
+        # the compute of the next ranges.  The ranges are small at both ends (_range_weights); everything
+        # launch-invariant is prepared once.
         ranges = [(0, nstars, 0, ns)]
         if nstars * ns >= 4_000_000 and self._d2h_chunks > 1:
             by_star = nstars >= self._d2h_chunks // 2
             total = nstars if by_star else ns
             n_chunks = min(total, self._d2h_chunks)
-            w = 0.7 ** np.arange(n_chunks)
+            w = self._range_weights(n_chunks)
             bounds = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * total)]).astype(np.int64)
             if not by_star:
                 bounds[1:-1] = (bounds[1:-1] + 2047) // 4096 * 4096        # whole blocks of samples
@@ -529,6 +530,17 @@ class BiasCorr(dv.LazyArrays):
                               det={(float(delta_RV), float(n_sigma_RV)): (det, bits, chunks)} if d_err is not None else {},
                               counters=counters, per_star=per_star, pop=launch.pop, err_fp=self._errors_fingerprint())
         self._set_device("delta_rv", drv)
+
+    @staticmethod
+    def _range_weights(n):
+        """Relative sizes of the ranges a large pass is launched in: small at BOTH ends.  The host side of a
+        range (copy + widening of its flags) starts when its kernel ends and the ranges' host work is
+        serial, so the pass takes  kernel(first range) + max(host work, remaining kernels) + host(last
+        range): the first range delays the start of the host pipeline (it dominates when the host is the
+        slower side -- eight ranks sharing one host's memory system), the last one is the tail nothing
+        overlaps (it dominates when the GPU is the slower side -- one rank)."""
+        k = np.arange(n, dtype=np.float64)
+        return np.minimum(1.6 ** k, 1.6 ** (n - 1 - k))
 
     def _fused_launcher(self, max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
                         per_star, bits=None, pop=None):

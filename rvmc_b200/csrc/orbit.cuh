@@ -183,9 +183,12 @@ RVMC_HD float rv_shape_f32(float e, float rome2, float sE, float cE, float sw, f
 // GUARD = false compiles the guard out: the host proves it unreachable when the largest
 // amplification the eccentricity bounds allow, sqrt(1-e^2)/(1-e)^2 at e_max, stays below guard_amp
 // (true for the reference's bounds: 43.6 at e = 0.9 against the default threshold 64).
+// `aresid` returns |E - e sin E - M| of the fp32 solve (0 on the guard path): callers that evaluate several
+// epochs of one orbit keep a running maximum and test it once (one FMNMX per epoch instead of a compare
+// and a predicated add).
 template <int ITERS = 0, bool GUARD = true>
-RVMC_HD float kepler_shape_f32(float M, double M64, bool neg, float e, float rome2, float sw, float cw,
-                               int iters, float guard_amp, int& guard, int& bad) {
+RVMC_HD float kepler_shape_resid_f32(float M, double M64, bool neg, float e, float rome2, float sw, float cw,
+                                     int iters, float guard_amp, int& guard, float& aresid) {
     float sE, cE, resid;
     const float E = kepler_f32<ITERS>(M, e, iters, sE, cE, resid);
     const float dd = fmaf(-e, cE, 1.0f);
@@ -198,12 +201,21 @@ RVMC_HD float kepler_shape_f32(float M, double M64, bool neg, float e, float rom
         const double cnu = (c64 - e64) * rd;
         const double snu = sqrt((1.0 - e64) * (1.0 + e64)) * s64 * rd;
         guard = 1;
-        bad = 0;
+        aresid = 0.0f;
         return (float)(cnu * (double)cw - snu * (double)sw + e64 * (double)cw);
     }
     guard = 0;
-    bad = (fabsf(resid) > 1e-5f) ? 1 : 0;
+    aresid = fabsf(resid);
     return rv_shape_f32(e, rome2, neg ? -sE : sE, cE, sw, cw);
+}
+template <int ITERS = 0, bool GUARD = true>
+RVMC_HD float kepler_shape_f32(float M, double M64, bool neg, float e, float rome2, float sw, float cw,
+                               int iters, float guard_amp, int& guard, int& bad) {
+    float aresid;
+    const float shape = kepler_shape_resid_f32<ITERS, GUARD>(M, M64, neg, e, rome2, sw, cw, iters, guard_amp, guard,
+                                                             aresid);
+    bad = (aresid > 1e-5f) ? 1 : 0;
+    return shape;
 }
 
 // Full single-epoch orbital RV of one sampled orbit [km/s]; the sign of the phase folds M into

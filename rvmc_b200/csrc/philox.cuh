@@ -109,7 +109,18 @@ RVMC_HD u32x4 philox_block(uint64_t seed, uint64_t item, uint32_t stream, uint32
 
 // 24-bit uniforms.  Both precisions consume the SAME value u = (w >> 8) * 2^-24 (exact in fp32),
 // so the fp32 fused path and the fp64 materialised path see identical draws.
+#if defined(RVMC_U01_MAGIC) && defined(__CUDA_ARCH__)
+// Experiment (not the default): the same 24-bit value without an I2F on the XU pipe -- the top 23 bits through
+// the 2^23 exponent trick, the last bit added by an FFMA.  6 ALU/FMA instructions against SHF + I2F + FMUL;
+// measured SLOWER on B200 (the kernels are issue-bound, not XU-bound).
+RVMC_HD float u01_f32(uint32_t w) {
+    const uint32_t x = w >> 8;
+    const float hi = __uint_as_float(0x4b000000u | (x >> 1)) - 8388608.0f;          // (x >> 1), exact
+    return fmaf(hi, 1.1920928955078125e-7f, (x & 1u) ? 5.9604644775390625e-8f : 0.0f);
+}
+#else
 RVMC_HD float u01_f32(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-8f; }        // [0,1)
+#endif
 RVMC_HD double u01_f64(uint32_t w) { return (double)(w >> 8) * 5.9604644775390625e-8; }
 RVMC_HD float u01_open_f32(uint32_t w) { return (float)((w >> 8) + 1u) * 5.9604644775390625e-8f; }  // (0,1]
 RVMC_HD double u01_open_f64(uint32_t w) { return (double)((w >> 8) + 1u) * 5.9604644775390625e-8; }

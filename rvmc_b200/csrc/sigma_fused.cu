@@ -633,6 +633,21 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) point_stats_kernel(StatsArgs
         const bool do_mode = nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX;
         const double last_edge = (double)nb_mode * a.bin;
         const float inv_bin = (float)(1.0 / a.bin);
+        // a bin width that is a power of two (the reference's 0.5, findBestDistributions.py:47) makes
+        // x / bin exact in fp32: floor(x / bin) is the bin and only the closed right end of the last bin
+        // (np.histogram) needs a clamp -- no fp64 edge comparison per element
+        int bin_exp;
+        const bool pow2_bin = frexp(a.bin, &bin_exp) == 0.5 && bin_exp > -100 && bin_exp < 100;
+        if (do_mode && pow2_bin) {
+            const int last = nb_mode - 1;
+            for_each([&](float x) {
+                const unsigned int bits = __float_as_uint(x);
+                const int g = table0[bits >> (32 - STATS_B0)];
+                if (g >= 0) atomicAdd(&histA[(g << STATS_B1) + ((bits >> STATS_B2) & ((1u << STATS_B1) - 1u))], 1u);
+                const int k = min((int)(x * inv_bin), last);     // NaN -> 0 here, but then nb_mode == 0 above
+                atomicAdd(&mode_hist[k], 1u);
+            });
+        } else
         for_each([&](float x) {
             const unsigned int bits = __float_as_uint(x);
             const int g = table0[bits >> (32 - STATS_B0)];

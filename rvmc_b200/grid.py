@@ -24,6 +24,7 @@ import numpy as np
 
 from . import _abi
 from . import _device as dv
+from ._trace import span
 
 M17_ERRORS = np.array([0.8, 2.3, 1.0, 1.8, 0.8, 1.0, 1.4, 2.5, 2.0, 0.4, 1.5, 0.6])   # findBestDistributions.py:292
 
@@ -309,10 +310,12 @@ def run_points(pops, seeds, measured_errors, sample_size, number_of_samples=10**
     with dv.DeviceGuard(dev):
         lib = _abi.lib()
         scratch = _scratch(lib, dev, ns) if sigma_d is None and nl else None
-        _abi.check(lib.rvmc_grid_run(pts, nl, dv.ptr(errd), int(sample_size), int(bool(weighted)), int(ddof), ns,
-                                     float(bin), int(hist_bins), dv.ptr(stats_d), dv.ptr(sigma_d), dv.ptr(hist_d),
-                                     dv.ptr(scratch), dv.ptr(counters), dv.stream_ptr(dev)))
-        stats = combine_point_stats(stats_d, local, n_points, 1, world, group).reshape(n_points)
+        with span("grid.points.kernels"):
+            _abi.check(lib.rvmc_grid_run(pts, nl, dv.ptr(errd), int(sample_size), int(bool(weighted)), int(ddof), ns,
+                                         float(bin), int(hist_bins), dv.ptr(stats_d), dv.ptr(sigma_d), dv.ptr(hist_d),
+                                         dv.ptr(scratch), dv.ptr(counters), dv.stream_ptr(dev)))
+        with span("grid.combine_stats"):
+            stats = combine_point_stats(stats_d, local, n_points, 1, world, group).reshape(n_points)
     out = dict(stats=stats, local=local, counters=dv.to_host(counters), sigma=None, hist=None)
     if sigma_d is not None:
         out["sigma"] = dv.to_host(sigma_d)
@@ -369,12 +372,14 @@ def run_points_fbins(pops, seeds, fbins, measured_errors, sample_size, number_of
             sigma_d = dv.empty((nl, nf, ns), "float32", dev) if keep_sigma and nl else None
             hist_d = dv.zeros((nl, nf, int(hist_bins)), "int32", dev) if keep_hist and nl else None
             scratch = _scratch(lib, dev, ns) if sigma_d is None and nl else None
-            _abi.check(lib.rvmc_grid_run_fbins(pts, nl, sub.ctypes.data_as(C.POINTER(C.c_double)), nf, dv.ptr(errd),
-                                               int(sample_size), int(bool(weighted)), int(ddof), ns, float(bin),
-                                               int(hist_bins), dv.ptr(stats_d), dv.ptr(sigma_d), dv.ptr(hist_d),
-                                               dv.ptr(scratch),
-                                               dv.ptr(counters), dv.stream_ptr(dev)))
-            part = combine_point_stats(stats_d, local, n_points, nf, world, group)
+            with span("grid.fbins.kernels"):
+                _abi.check(lib.rvmc_grid_run_fbins(pts, nl, sub.ctypes.data_as(C.POINTER(C.c_double)), nf,
+                                                   dv.ptr(errd), int(sample_size), int(bool(weighted)), int(ddof), ns,
+                                                   float(bin), int(hist_bins), dv.ptr(stats_d), dv.ptr(sigma_d),
+                                                   dv.ptr(hist_d), dv.ptr(scratch), dv.ptr(counters),
+                                                   dv.stream_ptr(dev)))
+            with span("grid.combine_stats"):
+                part = combine_point_stats(stats_d, local, n_points, nf, world, group)
             if nf == fb.size:
                 stats_all = part
             else:
@@ -662,6 +667,8 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
     o_vals = [v for k, v in zip(names, vals) if fused_axis is None or k != "fbin"]
     o_shape = tuple(len(v) for v in o_vals)
     n_points = int(np.prod(o_shape)) if o_shape else 1
+    _build = span("grid_search.build_share")
+    _build.__enter__()
     # this rank's share of the points, by cost: only an un-fused f_bin axis makes points differ in cost
     # (cost = sample_size * fbin); the deal is computed without enumerating the other ranks' points
     if fused_axis is None and "fbin" in o_names and world > 1:
@@ -676,6 +683,7 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
     pops = points_array(len(local), **cols)
     pops["seed"] = np.uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)
     pops["substream"] = 0 if common_random_numbers else local.astype(np.uint32)     # == with_streams on the full grid
+    _build.__exit__(None, None, None)
     if fused_axis is None:
         res = run_points(pops, None, _errs(measured_errors, sample_size), sample_size, number_of_samples, bin=bin,
                          ddof=ddof, device=device, group=group, distributed=distributed, local=local,
@@ -687,6 +695,8 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
                                number_of_samples, bin=bin, ddof=ddof, device=device, group=group,
                                distributed=distributed, local=local, n_points=n_points)
         stats = np.moveaxis(res["stats"].reshape(o_shape + (shape[fused_axis],)), -1, fused_axis)
+    _post = span("grid_search.best_fit")
+    _post.__enter__()
     out = dict(axes=dict(zip(names, vals)), shape=shape, stats=stats, counters=res["counters"],
                n_local=len(res["local"]), fbin_axis_fused=fused_axis is not None)
     if observed_sigma is not None:
@@ -703,6 +713,7 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
         out["best_index"] = tuple(int(v) for v in np.unravel_index(idx, shape))
         out["best_params"] = {k: float(v[j]) for k, v, j in zip(names, vals, out["best_index"])}
         out["best_distance"] = best
+    _post.__exit__(None, None, None)
     return out
 
 
