@@ -18,8 +18,6 @@
 // mean anomaly is fp32: closed-form starter + Halley, closed-form true anomaly, RV.  Noise is
 // one Philox block per six epochs.  max/min and the pairwise test are taken in registers; only
 // Delta-RV (4 B) and the detection flag (1 B) per binary reach HBM, and both are optional.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "pop_derive.h"
 
@@ -35,7 +33,7 @@ struct BcArgs {
     PhiloxKey key, noise_key;     // expanded on the host: round keys are constant-bank operands
     uint64_t seed;                // (kept for the fp64 mass draw)
     int32_t nstars, max_epochs;
-    int32_t items_per_star;       // work items (chunks of BC_THREADS * spt samples) per star
+    int32_t star0;                // first star of this launch (gridDim.y is limited to 65535)
     int32_t spt;                  // samples per thread
     int32_t first_star;           // global index of local star 0 (RNG counter only)
     const int32_t* n_epochs;      // [nstars]
@@ -93,6 +91,11 @@ __device__ __forceinline__ void bc_noise6_f64(uint64_t seed, uint64_t item, uint
 // Each thread walks a.spt samples of its star (1..BC_MAX_SPT, chosen by the host so that the grid
 // still holds >= 8 blocks per SM), so the per-block prologue (epoch tables, pair thresholds, two
 // barriers) is amortised over BC_THREADS * spt binaries.  3 blocks/SM at <= 85 registers measured best.
+// PERSISTENT blocks (a grid of k blocks per SM, each walking a contiguous run of such chunks and
+// restaging the tables only when the star changes) were built and measured in round 2 (commit b0198e4):
+// 3.20 / 3.19 / 3.12 ms for k = 3 / 4 / 6 against 3.08 ms for this one-chunk-per-block grid on 10^8 x 6 --
+// the ~24 500 short-lived blocks are not the cost: freshly scheduled blocks keep the three resident blocks
+// of an SM in different phases of the per-binary instruction mix, blocks that start together do not.
 #ifndef BC_MAX_SPT
 #define BC_MAX_SPT 16
 #endif
@@ -106,273 +109,246 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
     __shared__ float thr_s[NE * NE];      // pair thresholds max(delta_RV, n_sigma sqrt(ea^2+eb^2))
     __shared__ int uniform_s;
     __shared__ unsigned int c_det, c_guard, c_bad;
-    __shared__ unsigned long long units_s;    // binary-epoch RVs of the items walked for the staged star
 
     constexpr int ITERS = FAST ? 1 : 0;
     constexpr bool GUARD = !FAST;
+    const int star = a.star0 + (int)blockIdx.y;
+    const int ne = a.n_epochs[star];
+    RVMC_DEV_ASSERT(star >= 0 && star < a.nstars && ne >= 0 && ne <= NE && ne <= a.max_epochs);
     const bool noisy = FAST ? NOISY : (a.rv_err != nullptr);
     const bool quirk = FAST ? QUIRK : (a.quirk_phase != 0);
     float* const rv_out = (FAST && !RVOUT) ? nullptr : a.rv_out;
-    const int lane = threadIdx.x & 31;
 
-    // Work items: (star, chunk of BC_THREADS * spt samples), star-major.  Block b owns the CONTIGUOUS
-    // items [w0, w1): with one block per item this is the plain grid; with a grid of a few blocks per SM
-    // (persistent blocks, the default for large passes) a block walks ~total/grid items and meets a new
-    // star -- tables restaged, counters flushed, two barriers each -- only a few times in its life instead
-    // of once per 4096 binaries.
-    const int64_t total = (int64_t)a.items_per_star * a.nstars;
-    const int64_t base = total / gridDim.x, extra = total - base * gridDim.x;
-    const int64_t w0 = base * blockIdx.x + min((int64_t)blockIdx.x, extra);
-    int remaining = (int)base + (((int64_t)blockIdx.x < extra) ? 1 : 0);
-    int star = (int)(w0 / a.items_per_star);
-    int chunk = (int)(w0 - (int64_t)star * a.items_per_star);
-    int ne = 0;
-    bool need_stage = true;
+    if (threadIdx.x < ne) {
+        const double t = a.t_obs[(size_t)star * a.max_epochs + threadIdx.x];
+        A_s[threadIdx.x] = quirk ? RVMC_TWO_PI * t : t;
+        err_s[threadIdx.x] = noisy ? a.rv_err[(size_t)star * a.max_epochs + threadIdx.x] : 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        c_det = 0;
+        c_guard = 0;
+        c_bad = 0;
+    }
+    __syncthreads();
+    if (noisy) {
+        for (int p = threadIdx.x; p < ne * ne; p += blockDim.x) {
+            const int x = p / ne, y = p - x * ne;
+            const float ex = err_s[x], ey = err_s[y];
+            thr_s[x * NE + y] = fmaxf(a.delta_rv_min, a.n_sigma * sqrtf(fmaf(ex, ex, ey * ey)));
+        }
+        if (threadIdx.x == 0) {
+            int u = 1;
+            for (int k = 1; k < ne; ++k) u &= (err_s[k] == err_s[0]);
+            uniform_s = u;
+        }
+    }
+    __syncthreads();
+
     unsigned int my_guard = 0, my_bad = 0, my_det = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t i_first = (int64_t)blockIdx.x * (BC_THREADS * a.spt) + threadIdx.x;
+#pragma unroll 1
+    for (int rep = 0; rep < a.spt; ++rep) {
+        const int64_t i = i_first + (int64_t)rep * BC_THREADS;
+        if (i >= a.n_samples) break;
+        const uint64_t sample = a.first_sample + (uint64_t)i;
+        const uint64_t item = bc_item(a.first_star + star, sample);
+        const u32x4 wa = philox_block(a.key, item, RVMC_STREAM_ORBIT_A, 0);
+        const u32x4 wb = philox_block(a.key, item, RVMC_STREAM_ORBIT_B, 0);
 
-    // counters of the current star -> global (one atomic per block and star)
-    auto flush = [&]() {
+        // ---- per-binary quantities --------------------------------------------------------------
+        OrbitF32 o;
+        if (a.mass_mode == 0) {
+            const float p = fmaf(a.P32.mass.b, u01_f32(wa.x), a.P32.mass.a);
+            o.log2m = (a.P32.mass.kind == POW_ONE) ? fast_lg2(a.P32.mass.minv * p)
+                                                   : fmaf(a.P32.mass.inv, fast_lg2(p), a.P32.log2_mass_min);
+        } else {
+            // masses at face value (:190) or N(masses, mass_errors) (:183); the normal is the fp32
+            // Box-Muller of the SAME words rvmc_biascorr_sample uses (1e-7 relative apart): the hot
+            // kernel stays free of fp64 transcendentals and of the function calls they bring
+            double m = a.masses[star];
+            if (a.mass_mode == 1) {
+                const u32x4 w = philox_block(a.key, item >> 1, RVMC_STREAM_MASS, 0);
+                float z0, z1;
+                box_muller_f32(w.x, w.y, z0, z1);
+                m = fma(a.mass_errors[star], (double)((item & 1) ? z1 : z0), m);
+            }
+            o.log2m = fast_lg2((float)(m * (1.0 / RVMC_MSUN_KG)));     // m <= 0 -> NaN like the reference (Q12)
+        }
+        // Period in fp64: the phase needs ~1e-10 relative on P (2 pi t / P reaches ~2e3 turns).  Only
+        // 1/P is ever needed: time = u P (RVMC_bias_corr.py:328), so t / P = t_obs / P + u, and the
+        // eccentricity regimes compare log10 P.
+        double xd;
+        if constexpr (FAST) {
+            // exponent 1 or 2 (pi = 0 or the Sana et al. -0.5) directly, any other by the call-free
+            // pow_bounded_f64: no pow(), no call, no stack frame
+            const double p = __dadd_rn(a.P64.logp.a, __dmul_rn(a.P64.logp.b, u01_f64(wa.y)));
+            const double pw = (a.P64.logp.kind == POW_ONE) ? p
+                              : (a.P64.logp.kind == POW_TWO) ? p * p : pow_bounded_f64(p, a.P64.logp.inv);
+            xd = pw * a.P64.logp.minv;
+        } else {
+            xd = powerlaw_f64(a.P64.logp, u01_f64(wa.y));
+        }
+        const double invP = exp10_fast_f64(-4.9365137424788932 - xd);   // 1 / (86400 * 10^x)  [1/s]
+        o.x = (float)xd;
+        const double uphase = u01_f64(wa.z);
+        o.q = powerlaw_f32(a.P32.q, u01_f32(wa.w));
+        {
+            const float ue = u01_f32(wb.x);
+            const bool is_long = xd > a.P64.x_mid;
+            const float e = powerlaw_f32(is_long ? a.P32.e_long : a.P32.e_mid, ue);
+            o.e = (xd > a.P64.x_circ) ? e : 0.0f;
+        }
+        o.cosi = u01_f32(wb.y);
+        o.sini = fast_sqrt((1.0f - o.cosi) * (1.0f + o.cosi));
+        o.wturn = u01_f32(wb.z);
+        const float K = semi_amplitude_f32(a.P32, o);
+        float sw, cw;
+        sincos_turn(o.wturn, sw, cw);
+        const float Ksw = K * sw, Kcw = K * cw;
+        const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
+        const double c0 = quirk ? RVMC_TWO_PI * uphase : uphase;
+
+        // ---- epochs -----------------------------------------------------------------------------
+        float rvs[NE];
+        float vmax = -INFINITY, vmin = INFINITY;
+        float z[6];
+        float res_max = 0.0f;             // largest Kepler residual over the epochs of this binary
+        auto epoch = [&](int k) {
+            if (noisy && (k % 6) == 0) bc_noise6_f32(a.noise_key, item, RVMC_STREAM_EPOCH, k / 6, z);
+            float M;
+            double M64;
+            bool neg = false;
+            // quirk (RVMC_bias_corr.py:357): ((2 pi t) mod P) / P == frac(2 pi t_obs / P + 2 pi u), in
+            // [0,1) and used as radians; physical: 2 pi frac(t_obs / P + u)
+            const double v = fma(A_s[k], invP, c0);
+            const double fr = v - floor(v);
+            if (quirk) {
+                M64 = fr;
+            } else {
+                const double fold = fr - rint(fr);                  // [-0.5, 0.5]
+                neg = fold < 0.0;
+                M64 = RVMC_TWO_PI * fabs(fold);
+            }
+            M = (float)M64;
+            int g;
+            float ar;
+            // K is folded into the orientation terms (the shape is linear in sin/cos omega)
+            float rv = kepler_shape_resid_f32<ITERS, GUARD>(M, M64, neg, o.e, rome2, Ksw, Kcw, a.kepler_iters,
+                                                            a.P32.guard_amp, g, ar);
+            my_guard += g;
+            res_max = fmaxf(res_max, ar);
+            if (noisy) rv = fmaf(err_s[k], z[k % 6], rv);
+            rvs[k] = rv;
+            vmax = fmaxf(vmax, rv);
+            vmin = fminf(vmin, rv);
+            if (rv_out) rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
+        };
+        if constexpr (NE <= 16) {
+            // fully unrolled: rvs[] and z[] live in registers; a star with exactly NE epochs (the common
+            // case: NE is chosen from max_epochs) takes the branch-free copy
+            if (ne == NE) {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) epoch(k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NE; ++k)
+                    if (k < ne) epoch(k);
+            }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < ne; ++k) epoch(k);
+        }
+        my_bad += (res_max > 1e-5f) ? 1u : 0u;
+        // np.max/np.min propagate NaN (mass draw <= 0, Q12); fmaxf/fminf would drop it
+        float drv = vmax - vmin;
+        if (K != K) drv = K;
+        if (a.delta_rv) a.delta_rv[(size_t)star * a.sample_stride + i] = drv;
+
+        // ---- significance test --------------------------------------------------------------------
+        bool det = false;
+        if (noisy) {
+            if (uniform_s) {
+                // equal errors: every pair has the same threshold, so the largest difference decides
+                det = (ne >= 2) && (drv > thr_s[1]);
+            } else if constexpr (NE <= 16) {
+#pragma unroll
+                for (int x = 0; x < NE; ++x)
+#pragma unroll
+                    for (int y = x + 1; y < NE; ++y)
+                        if (y < ne) det = det || (fabsf(rvs[x] - rvs[y]) > thr_s[x * NE + y]);
+            } else {
+                for (int x = 0; x < ne; ++x)
+                    for (int y = x + 1; y < ne; ++y) det = det || (fabsf(rvs[x] - rvs[y]) > thr_s[x * NE + y]);
+            }
+        }
+        if (a.detected) a.detected[(size_t)star * a.sample_stride + i] = det ? 1 : 0;
+        if (a.det_bits) {
+            // RVMC_bias_corr.py:476 returns one bool per binary: one BIT of it leaves the chip.  A warp holds
+            // 32 consecutive samples; the lanes past the end of a ragged last warp have left the loop and are
+            // not named in the mask, so their bits are 0.
+            const int64_t left = a.n_samples - (i - lane);          // warp-uniform
+            unsigned int word;
+            if (left >= 32) word = __ballot_sync(0xffffffffu, det);
+            else word = __ballot_sync((1u << (int)left) - 1u, det);   // a computed mask costs ~30 instructions: tail only
+            if (lane == 0) a.det_bits[(size_t)star * a.bits_stride + (i >> 5)] = word;
+        }
+        my_det += det ? 1u : 0u;
+    }
+
+    // ---- counters ---------------------------------------------------------------------------------
+    if (a.counters || a.det_per_star) {
         for (int off = 16; off > 0; off >>= 1) my_det += __shfl_xor_sync(0xffffffffu, my_det, off);
-        if (lane == 0 && my_det) atomicAdd(&c_det, my_det);
+        if ((threadIdx.x & 31) == 0 && my_det) atomicAdd(&c_det, my_det);
         if (my_guard) atomicAdd(&c_guard, my_guard);
         if (my_bad) atomicAdd(&c_bad, my_bad);
-        my_det = my_guard = my_bad = 0;
         __syncthreads();
         if (threadIdx.x == 0) {
+            const int64_t first = (int64_t)blockIdx.x * (BC_THREADS * a.spt);
+            const int64_t nvalid = min((int64_t)(BC_THREADS * a.spt), a.n_samples - first);
             if (a.counters) {
-                atomicAdd(a.counters + 0, units_s);
+                atomicAdd(a.counters + 0, (unsigned long long)(nvalid * ne));
                 if (c_det) atomicAdd(a.counters + 1, (unsigned long long)c_det);
                 if (c_guard) atomicAdd(a.counters + 2, (unsigned long long)c_guard);
                 if (c_bad) atomicAdd(a.counters + 3, (unsigned long long)c_bad);
             }
             if (a.det_per_star && c_det) atomicAdd(a.det_per_star + star, c_det);
         }
-    };
-    // epoch tables and pair thresholds of `star` -> shared memory
-    auto stage = [&]() {
-        __syncthreads();                  // everybody is done with the previous star's tables and counters
-        ne = a.n_epochs[star];
-        RVMC_DEV_ASSERT(star >= 0 && star < a.nstars && ne >= 0 && ne <= NE && ne <= a.max_epochs);
-        if (threadIdx.x < ne) {
-            const double t = a.t_obs[(size_t)star * a.max_epochs + threadIdx.x];
-            A_s[threadIdx.x] = quirk ? RVMC_TWO_PI * t : t;
-            err_s[threadIdx.x] = noisy ? a.rv_err[(size_t)star * a.max_epochs + threadIdx.x] : 0.0f;
-        }
-        if (threadIdx.x == 0) {
-            c_det = 0;
-            c_guard = 0;
-            c_bad = 0;
-            units_s = 0;
-        }
-        __syncthreads();
-        if (noisy) {
-            for (int p = threadIdx.x; p < ne * ne; p += blockDim.x) {
-                const int x = p / ne, y = p - x * ne;
-                const float ex = err_s[x], ey = err_s[y];
-                thr_s[x * NE + y] = fmaxf(a.delta_rv_min, a.n_sigma * sqrtf(fmaf(ex, ex, ey * ey)));
-            }
-            if (threadIdx.x == 0) {
-                int u = 1;
-                for (int k = 1; k < ne; ++k) u &= (err_s[k] == err_s[0]);
-                uniform_s = u;
-            }
-        }
-        __syncthreads();
-        need_stage = false;
-    };
-
-    const bool counting = a.counters || a.det_per_star;
-#pragma unroll 1
-    for (; remaining > 0; --remaining) {
-        if (need_stage) stage();          // block-uniform
-        const int64_t c_first = (int64_t)chunk * (BC_THREADS * a.spt);
-        if (threadIdx.x == 0)
-            units_s += (unsigned long long)(min((int64_t)(BC_THREADS * a.spt), a.n_samples - c_first) * ne);
-        const int64_t i_first = c_first + threadIdx.x;
-#pragma unroll 1
-        for (int rep = 0; rep < a.spt; ++rep) {
-            const int64_t i = i_first + (int64_t)rep * BC_THREADS;
-            if (i >= a.n_samples) break;
-            const uint64_t sample = a.first_sample + (uint64_t)i;
-            const uint64_t item = bc_item(a.first_star + star, sample);
-            const u32x4 wa = philox_block(a.key, item, RVMC_STREAM_ORBIT_A, 0);
-            const u32x4 wb = philox_block(a.key, item, RVMC_STREAM_ORBIT_B, 0);
-
-            // ---- per-binary quantities --------------------------------------------------------------
-            OrbitF32 o;
-            if (a.mass_mode == 0) {
-                const float p = fmaf(a.P32.mass.b, u01_f32(wa.x), a.P32.mass.a);
-                o.log2m = (a.P32.mass.kind == POW_ONE) ? fast_lg2(a.P32.mass.minv * p)
-                                                       : fmaf(a.P32.mass.inv, fast_lg2(p), a.P32.log2_mass_min);
-            } else {
-                // masses at face value (:190) or N(masses, mass_errors) (:183); the normal is the fp32
-                // Box-Muller of the SAME words rvmc_biascorr_sample uses (1e-7 relative apart): the hot
-                // kernel stays free of fp64 transcendentals and of the function calls they bring
-                double m = a.masses[star];
-                if (a.mass_mode == 1) {
-                    const u32x4 w = philox_block(a.key, item >> 1, RVMC_STREAM_MASS, 0);
-                    float z0, z1;
-                    box_muller_f32(w.x, w.y, z0, z1);
-                    m = fma(a.mass_errors[star], (double)((item & 1) ? z1 : z0), m);
-                }
-                o.log2m = fast_lg2((float)(m * (1.0 / RVMC_MSUN_KG)));     // m <= 0 -> NaN like the reference (Q12)
-            }
-            // Period in fp64: the phase needs ~1e-10 relative on P (2 pi t / P reaches ~2e3 turns).  Only
-            // 1/P is ever needed: time = u P (RVMC_bias_corr.py:328), so t / P = t_obs / P + u, and the
-            // eccentricity regimes compare log10 P.
-            double xd;
-            if constexpr (FAST) {
-                // exponent 1 or 2 (pi = 0 or the Sana et al. -0.5) directly, any other by the call-free
-                // pow_bounded_f64: no pow(), no call, no stack frame
-                const double p = __dadd_rn(a.P64.logp.a, __dmul_rn(a.P64.logp.b, u01_f64(wa.y)));
-                const double pw = (a.P64.logp.kind == POW_ONE) ? p
-                                  : (a.P64.logp.kind == POW_TWO) ? p * p : pow_bounded_f64(p, a.P64.logp.inv);
-                xd = pw * a.P64.logp.minv;
-            } else {
-                xd = powerlaw_f64(a.P64.logp, u01_f64(wa.y));
-            }
-            const double invP = exp10_fast_f64(-4.9365137424788932 - xd);   // 1 / (86400 * 10^x)  [1/s]
-            o.x = (float)xd;
-            const double uphase = u01_f64(wa.z);
-            o.q = powerlaw_f32(a.P32.q, u01_f32(wa.w));
-            {
-                const float ue = u01_f32(wb.x);
-                const bool is_long = xd > a.P64.x_mid;
-                const float e = powerlaw_f32(is_long ? a.P32.e_long : a.P32.e_mid, ue);
-                o.e = (xd > a.P64.x_circ) ? e : 0.0f;
-            }
-            o.cosi = u01_f32(wb.y);
-            o.sini = fast_sqrt((1.0f - o.cosi) * (1.0f + o.cosi));
-            o.wturn = u01_f32(wb.z);
-            const float K = semi_amplitude_f32(a.P32, o);
-            float sw, cw;
-            sincos_turn(o.wturn, sw, cw);
-            const float Ksw = K * sw, Kcw = K * cw;
-            const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
-            const double c0 = quirk ? RVMC_TWO_PI * uphase : uphase;
-
-            // ---- epochs -----------------------------------------------------------------------------
-            float rvs[NE];
-            float vmax = -INFINITY, vmin = INFINITY;
-            float z[6];
-            float res_max = 0.0f;         // largest Kepler residual over the epochs of this binary
-            auto epoch = [&](int k) {
-                if (noisy && (k % 6) == 0) bc_noise6_f32(a.noise_key, item, RVMC_STREAM_EPOCH, k / 6, z);
-                float M;
-                double M64;
-                bool neg = false;
-                // quirk (RVMC_bias_corr.py:357): ((2 pi t) mod P) / P == frac(2 pi t_obs / P + 2 pi u), in
-                // [0,1) and used as radians; physical: 2 pi frac(t_obs / P + u)
-                const double v = fma(A_s[k], invP, c0);
-                const double fr = v - floor(v);
-                if (quirk) {
-                    M64 = fr;
-                } else {
-                    const double fold = fr - rint(fr);                  // [-0.5, 0.5]
-                    neg = fold < 0.0;
-                    M64 = RVMC_TWO_PI * fabs(fold);
-                }
-                M = (float)M64;
-                int g;
-                float ar;
-                // K is folded into the orientation terms (the shape is linear in sin/cos omega)
-                float rv = kepler_shape_resid_f32<ITERS, GUARD>(M, M64, neg, o.e, rome2, Ksw, Kcw, a.kepler_iters,
-                                                                a.P32.guard_amp, g, ar);
-                my_guard += g;
-                res_max = fmaxf(res_max, ar);
-                if (noisy) rv = fmaf(err_s[k], z[k % 6], rv);
-                rvs[k] = rv;
-                vmax = fmaxf(vmax, rv);
-                vmin = fminf(vmin, rv);
-                if (rv_out) rv_out[((size_t)star * a.max_epochs + k) * a.sample_stride + i] = rv;
-            };
-            if constexpr (NE <= 16) {
-                // fully unrolled: rvs[] and z[] live in registers; a star with exactly NE epochs (the common
-                // case: NE is chosen from max_epochs) takes the branch-free copy
-                if (ne == NE) {
-    #pragma unroll
-                    for (int k = 0; k < NE; ++k) epoch(k);
-                } else {
-    #pragma unroll
-                    for (int k = 0; k < NE; ++k)
-                        if (k < ne) epoch(k);
-                }
-            } else {
-    #pragma unroll 1
-                for (int k = 0; k < ne; ++k) epoch(k);
-            }
-            my_bad += (res_max > 1e-5f) ? 1u : 0u;
-            // np.max/np.min propagate NaN (mass draw <= 0, Q12); fmaxf/fminf would drop it
-            float drv = vmax - vmin;
-            if (K != K) drv = K;
-            if (a.delta_rv) a.delta_rv[(size_t)star * a.sample_stride + i] = drv;
-
-            // ---- significance test --------------------------------------------------------------------
-            bool det = false;
-            if (noisy) {
-                if (uniform_s) {
-                    // equal errors: every pair has the same threshold, so the largest difference decides
-                    det = (ne >= 2) && (drv > thr_s[1]);
-                } else if constexpr (NE <= 16) {
-    #pragma unroll
-                    for (int x = 0; x < NE; ++x)
-    #pragma unroll
-                        for (int y = x + 1; y < NE; ++y)
-                            if (y < ne) det = det || (fabsf(rvs[x] - rvs[y]) > thr_s[x * NE + y]);
-                } else {
-                    for (int x = 0; x < ne; ++x)
-                        for (int y = x + 1; y < ne; ++y) det = det || (fabsf(rvs[x] - rvs[y]) > thr_s[x * NE + y]);
-                }
-            }
-            if (a.detected) a.detected[(size_t)star * a.sample_stride + i] = det ? 1 : 0;
-            if (a.det_bits) {
-                // RVMC_bias_corr.py:476 returns one bool per binary: one BIT of it leaves the chip.  A warp holds
-                // 32 consecutive samples; the lanes past the end of a ragged last warp have left the loop and are
-                // not named in the mask, so their bits are 0.
-                const int64_t left = a.n_samples - (i - lane);          // warp-uniform
-                unsigned int word;
-                if (left >= 32) word = __ballot_sync(0xffffffffu, det);
-                else word = __ballot_sync((1u << (int)left) - 1u, det);   // a computed mask costs ~30 instructions: tail only
-                if (lane == 0) a.det_bits[(size_t)star * a.bits_stride + (i >> 5)] = word;
-            }
-            my_det += det ? 1u : 0u;
-        }
-        if (++chunk == a.items_per_star) {      // the star is finished: its counters go out, the next one is staged
-            if (counting) flush();
-            chunk = 0;
-            ++star;
-            need_stage = true;
-        }
     }
-    if (counting && !need_stage) flush();
 }
 
 template <int NE, bool FAST, bool QUIRK, bool RVOUT, bool NOISY>
-static int bc_launch(BcArgs& a, unsigned int grid, cudaStream_t stream) {
-    biascorr_fused_kernel<NE, FAST, QUIRK, RVOUT, NOISY><<<grid, BC_THREADS, 0, stream>>>(a);
-    RVMC_LAUNCH_CHECK();
+static int bc_launch(BcArgs& a, int64_t blocks_per_star, cudaStream_t stream) {
+    // gridDim.y carries the star (<= 65535 per launch)
+    for (int s0 = 0; s0 < a.nstars; s0 += 65535) {
+        a.star0 = s0;
+        const int ny = a.nstars - s0 < 65535 ? a.nstars - s0 : 65535;
+        biascorr_fused_kernel<NE, FAST, QUIRK, RVOUT, NOISY>
+            <<<dim3((unsigned int)blocks_per_star, (unsigned int)ny), BC_THREADS, 0, stream>>>(a);
+        RVMC_LAUNCH_CHECK();
+    }
     return RVMC_OK;
 }
 
 template <int NE>
-static int bc_dispatch(BcArgs& a, bool guard, unsigned int grid, cudaStream_t stream) {
+static int bc_dispatch(BcArgs& a, bool guard, int64_t blocks_per_star, cudaStream_t stream) {
     if constexpr (NE <= 16) {
         // launch-uniform switches -> template arguments (phase convention, RVs written, errors given)
         if (a.kepler_iters == 1 && !guard) {
             const int sel = (a.quirk_phase ? 4 : 0) | (a.rv_out ? 2 : 0) | (a.rv_err ? 1 : 0);
             switch (sel) {
-                case 0: return bc_launch<NE, true, false, false, false>(a, grid, stream);
-                case 1: return bc_launch<NE, true, false, false, true>(a, grid, stream);
-                case 2: return bc_launch<NE, true, false, true, false>(a, grid, stream);
-                case 3: return bc_launch<NE, true, false, true, true>(a, grid, stream);
-                case 4: return bc_launch<NE, true, true, false, false>(a, grid, stream);
-                case 5: return bc_launch<NE, true, true, false, true>(a, grid, stream);
-                case 6: return bc_launch<NE, true, true, true, false>(a, grid, stream);
-                default: return bc_launch<NE, true, true, true, true>(a, grid, stream);
+                case 0: return bc_launch<NE, true, false, false, false>(a, blocks_per_star, stream);
+                case 1: return bc_launch<NE, true, false, false, true>(a, blocks_per_star, stream);
+                case 2: return bc_launch<NE, true, false, true, false>(a, blocks_per_star, stream);
+                case 3: return bc_launch<NE, true, false, true, true>(a, blocks_per_star, stream);
+                case 4: return bc_launch<NE, true, true, false, false>(a, blocks_per_star, stream);
+                case 5: return bc_launch<NE, true, true, false, true>(a, blocks_per_star, stream);
+                case 6: return bc_launch<NE, true, true, true, false>(a, blocks_per_star, stream);
+                default: return bc_launch<NE, true, true, true, true>(a, blocks_per_star, stream);
             }
         }
     }
-    return bc_launch<NE, false, false, true, true>(a, grid, stream);
+    return bc_launch<NE, false, false, true, true>(a, blocks_per_star, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -589,6 +565,7 @@ int rvmc_biascorr_fused_packed(const rvmc_pop_params* p, uint64_t seed, uint64_t
     a.noise_key = philox_key(noise_seed);
     a.nstars = nstars;
     a.max_epochs = max_epochs;
+    a.star0 = 0;
     a.first_star = first_star;
     a.n_epochs = n_epochs;
     a.t_obs = t_obs;
@@ -610,42 +587,21 @@ int rvmc_biascorr_fused_packed(const rvmc_pop_params* p, uint64_t seed, uint64_t
     a.rv_out = rv_out;
     a.counters = (unsigned long long*)counters;
     a.det_per_star = det_per_star;
-    // Launch geometry.  Small passes: one block per work item, the samples per thread chosen so that the
-    // grid still holds >= 8 blocks per SM.  Large passes: PERSISTENT blocks -- a grid of BC_MIN_BLOCKS blocks
-    // per SM, each walking a contiguous run of work items (>= 64 of them, so that the static split is even
-    // to ~1 %); the per-star staging and the counter flush then run a few times per block, not once per
-    // 4096 binaries.  RVMC_BC_PERSIST = 0 / k forces one block per item / k blocks per SM (tuning).
-    const int64_t binaries = (int64_t)nstars * n_samples;
-    const int sms = sm_count();
-    static const int persist_env = [] {
-        const char* e = getenv("RVMC_BC_PERSIST");
-        return e ? atoi(e) : -1;
-    }();
-    int per_sm = persist_env >= 0 ? persist_env : BC_MIN_BLOCKS;
-    if (per_sm > 32) per_sm = 32;
-    int64_t spt = binaries / ((int64_t)BC_THREADS * sms * 8);
+    // samples per thread: as many as keep >= 8 blocks per SM in flight
+    int64_t spt = ((int64_t)nstars * n_samples) / ((int64_t)BC_THREADS * sm_count() * 8);
     spt = spt < 1 ? 1 : (spt > BC_MAX_SPT ? BC_MAX_SPT : spt);
-    bool persistent = per_sm > 0 && binaries >= (int64_t)BC_THREADS * sms * per_sm * 64;
-    if (persistent) {
-        spt = binaries / ((int64_t)BC_THREADS * sms * per_sm * 64);
-        spt = spt < 1 ? 1 : (spt > 8 ? 8 : spt);
-    }
     a.spt = (int32_t)spt;
-    const int64_t per_star = (n_samples + BC_THREADS * spt - 1) / (BC_THREADS * spt);
-    const int64_t items = per_star * nstars;
-    const int64_t grid64 = persistent ? (int64_t)sms * per_sm : items;
-    a.items_per_star = (int32_t)per_star;
-    if (grid64 > 0x7fffffffLL || per_star > 0x7fffffffLL || items / grid64 >= 0x7fffffffLL) {
-        set_error("too many samples in one launch (%lld binaries); shard them", (long long)binaries);
+    const int64_t blocks_per_star = (n_samples + BC_THREADS * spt - 1) / (BC_THREADS * spt);
+    if (blocks_per_star > 0x7fffffffLL) {
+        set_error("too many samples in one launch (%lld); shard them", (long long)n_samples);
         return RVMC_ERR_UNSUPPORTED;
     }
-    const unsigned int grid = (unsigned int)grid64;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const bool guard = guard_reachable(*p);
-    if (max_epochs <= 6) return bc_dispatch<6>(a, guard, grid, stream);
-    if (max_epochs <= 8) return bc_dispatch<8>(a, guard, grid, stream);
-    if (max_epochs <= 16) return bc_dispatch<16>(a, guard, grid, stream);
-    return bc_dispatch<64>(a, guard, grid, stream);      // 17..64 epochs: run-time loops, RVs in local memory
+    if (max_epochs <= 6) return bc_dispatch<6>(a, guard, blocks_per_star, stream);
+    if (max_epochs <= 8) return bc_dispatch<8>(a, guard, blocks_per_star, stream);
+    if (max_epochs <= 16) return bc_dispatch<16>(a, guard, blocks_per_star, stream);
+    return bc_dispatch<64>(a, guard, blocks_per_star, stream);      // 17..64 epochs: run-time loops, RVs in local memory
 }
 
 int rvmc_biascorr_sample(const rvmc_pop_params* p, uint64_t seed, int nstars, int mass_mode, const double* masses,

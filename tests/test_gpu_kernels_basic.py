@@ -174,7 +174,7 @@ def test_to_host_staged_path_equals_the_direct_copy(monkeypatch):
     """Results above PIN_DIRECT_MAX are staged through two fixed pinned buffers into pageable memory
     (reading a multi-GB attribute must not grow the locked memory of the process)."""
     import torch
-    x = torch.arange(3_000_017, dtype=torch.float32, device=g.dev()).reshape(7, -1) * 0.5
+    x = torch.arange(7 * 428_573, dtype=torch.float32, device=g.dev()).reshape(7, -1) * 0.5
     want = x.cpu().numpy()
     monkeypatch.setattr(dv, "PIN_DIRECT_MAX", 1 << 20)
     monkeypatch.setattr(dv, "PIN_STAGE_BYTES", (1 << 20) + 4096)
