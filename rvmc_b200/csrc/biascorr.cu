@@ -146,11 +146,16 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
 
     unsigned int my_guard = 0, my_bad = 0, my_det = 0;
     const int lane = threadIdx.x & 31;
-    const int64_t i_first = (int64_t)blockIdx.x * (BC_THREADS * a.spt) + threadIdx.x;
+    // the block's samples are [block_base, block_base + limit); inside the loop the index is a 32-bit offset
+    const int64_t block_base = (int64_t)blockIdx.x * (BC_THREADS * a.spt);
+    const int limit = (int)min((int64_t)(BC_THREADS * a.spt), a.n_samples - block_base);
+    // word of the packed flags that holds this warp's samples of the first pass; BC_THREADS / 32 words further
+    // per pass.  Only lane 0 stores.
+    uint32_t* bits_w = a.det_bits ? a.det_bits + (size_t)star * a.bits_stride + (block_base >> 5) + (threadIdx.x >> 5)
+                                  : nullptr;
 #pragma unroll 1
-    for (int rep = 0; rep < a.spt; ++rep) {
-        const int64_t i = i_first + (int64_t)rep * BC_THREADS;
-        if (i >= a.n_samples) break;
+    for (int il = threadIdx.x; il < limit; il += BC_THREADS, bits_w += BC_THREADS / 32) {
+        const int64_t i = block_base + il;
         const uint64_t sample = a.first_sample + (uint64_t)i;
         const uint64_t item = bc_item(a.first_star + star, sample);
         const u32x4 wa = philox_block(a.key, item, RVMC_STREAM_ORBIT_A, 0);
@@ -286,12 +291,11 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
         if (a.det_bits) {
             // RVMC_bias_corr.py:476 returns one bool per binary: one BIT of it leaves the chip.  A warp holds
             // 32 consecutive samples; the lanes past the end of a ragged last warp have left the loop and are
-            // not named in the mask, so their bits are 0.
-            const int64_t left = a.n_samples - (i - lane);          // warp-uniform
+            // not named in the mask, so their bits are 0.  (a.det_bits is tested, not bits_w: launch-uniform)
             unsigned int word;
-            if (left >= 32) word = __ballot_sync(0xffffffffu, det);
-            else word = __ballot_sync((1u << (int)left) - 1u, det);   // a computed mask costs ~30 instructions: tail only
-            if (lane == 0) a.det_bits[(size_t)star * a.bits_stride + (i >> 5)] = word;
+            if ((il | 31) < limit) word = __ballot_sync(0xffffffffu, det);
+            else word = __ballot_sync((1u << (limit & 31)) - 1u, det);    // a computed mask costs ~30 instructions: tail only
+            if (lane == 0) *bits_w = word;
         }
         my_det += det ? 1u : 0u;
     }
