@@ -133,8 +133,9 @@ def _records(byte_tensor):
     """uint8 tensor holding rvmc_point_stats records -> writable NumPy structured array that owns its
     memory (one device-to-host copy, no further host copies)."""
     t = byte_tensor.detach()
-    host = t.cpu() if t.is_cuda else t.clone()
-    return host.numpy().view(STATS_DTYPE)
+    if t.is_cuda:
+        return dv.to_host(t).view(STATS_DTYPE)      # pinned destination above 1 MB: one DMA, no staging copy
+    return t.clone().numpy().view(STATS_DTYPE)
 
 
 def combine_point_stats(local_bytes, local, n_points, row_len, world, group=None):

@@ -6,6 +6,7 @@ or the host's own memory system?  Measured with N concurrent ranks (one per GPU)
   bits    : D2H of 12.5 MB of packed flags into pinned memory
   unpack  : rvmc_unpack_bits_host of those 12.5 MB into a 100 MB pinned bool array, T threads per rank
   both    : bits + unpack back to back (the cost of the packed route per pass)
+  hybridXX: XX % of the flags as bytes by DMA WHILE the CPU widens the packed rest (are the two walls independent?)
 
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 ... tools/d2h_bandwidth.py
 
@@ -39,6 +40,22 @@ REPS = 10
 
 
 def run(route, threads):
+    if route.startswith("hybrid"):
+        # a share of the flags as bytes by DMA, the rest as bits widened by the CPU -- both at the same time:
+        # are the two walls (PCIe/IOMMU path of the DMA, memory system under CPU stores) independent?
+        share = int(route[6:]) / 100.0
+        nb = int(N * share) // 4096 * 4096          # flags that travel as bytes
+        nw0 = nb // 32
+        for _ in range(REPS):
+            dst_bits[nw0:].copy_(src_bits[nw0:], non_blocking=True)        # the packed words first (small) ...
+            e_bits = torch.cuda.Event()
+            e_bits.record()
+            dst_bytes[:nb].copy_(src_bytes[:nb], non_blocking=True)        # ... then the byte block by DMA
+            e_bits.synchronize()
+            assert lib.rvmc_unpack_bits_host(dst_bits.data_ptr() + 4 * nw0, NW - nw0, 1, N - nb,
+                                             dst_bytes.data_ptr() + nb, N - nb, threads) == 0   # while the DMA runs
+            torch.cuda.synchronize()
+        return
     for _ in range(REPS):
         if route == "bytes":
             dst_bytes.copy_(src_bytes, non_blocking=True)
@@ -74,7 +91,8 @@ cores = len(os.sched_getaffinity(0))
 out = {"world": world, "host_cores": cores, "flags_per_pass": N, "unit": "GB/s of result bytes per rank"}
 run("both", 2)          # warm-up: pins, pool threads, page faults
 for route, threads in (("bytes", 0), ("bits", 0), ("unpack", 1), ("unpack", 2), ("unpack", 4), ("unpack", 8),
-                       ("both", 2), ("both", 4), ("both", 8)):
+                       ("both", 2), ("both", 4), ("both", 8), ("hybrid30", 2), ("hybrid30", 4), ("hybrid40", 2),
+                       ("hybrid40", 4), ("hybrid50", 2), ("hybrid50", 4)):
     if threads and threads * world > 2 * cores:
         continue
     alone = measure(route, threads, rank == 0)
