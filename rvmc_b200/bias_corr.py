@@ -15,6 +15,13 @@ Two execution modes, chosen automatically:
 The phase quirk of RVMC_bias_corr.py:357 (mean anomaly = ((2 pi t) mod P)/P) is
 reproduced by default; `physical_phase=True` uses 2 pi frac(t/P) instead.  Additive kwargs:
 `seed`, `device`, `physical_phase`.
+
+Precision of what the FUSED mode hands back: `delta_rv`, `radial_velocities` and the detection flags come
+from the fp32 kernel (per-orbit RVs within 1e-5 of the reference's fp64 arithmetic relative to
+max(|RV|, K)); `delta_rv` is a float32 array, `radial_velocities` float64 arrays holding float32-accurate
+values.  The REPLAY mode evaluates RVMC_bias_corr.py:406-422 in fp64 (1e-9) and returns float64.
+`get_detected_binaries()` returns the reference's `bool (n_stars, n_samples)`; on the way from the GPU the
+flags travel bit-packed (1/8 of the PCIe bytes) and are widened on the host (`flag_transfer`).
 """
 import ctypes as C
 import os

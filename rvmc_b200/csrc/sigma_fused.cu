@@ -486,6 +486,8 @@ struct StatsArgs {
     rvmc_point_stats* stats_out;
     uint32_t* hist_out;        // [n_points][hist_bins] or nullptr
     const uint32_t* fail;      // [n_points][2] {guard lanes, non-converged lanes} of the producer, or nullptr
+    uint8_t* todo;             // [n_points] or nullptr.  point_stats_fast_kernel sets todo[row] = 1 for the rows it
+                               // leaves to the general kernel, which (when todo is given) skips all others
 };
 
 __device__ __forceinline__ double block_sum_f64(double x, double* scratch) {
@@ -496,7 +498,7 @@ __device__ __forceinline__ double block_sum_f64(double x, double* scratch) {
     __syncthreads();
     double tot = 0.0;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STATS_THREADS / 32; ++i) tot += scratch[i];
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += scratch[i];
         scratch[0] = tot;
     }
     __syncthreads();
@@ -548,6 +550,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) point_stats_kernel(StatsArgs
     __shared__ int group0_of[STATS_TARGETS];
     __shared__ unsigned int max_bits;
 
+    if (a.todo && !a.todo[blockIdx.x]) return;      // done by point_stats_fast_kernel (block-uniform)
     const int64_t n = a.n_real;
     const float* __restrict__ sig = a.sigma + (size_t)blockIdx.x * a.sigma_stride;
     rvmc_point_stats* st = a.stats_out + blockIdx.x;
@@ -769,6 +772,340 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) point_stats_kernel(StatsArgs
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6, fast form: TWO reads of the row instead of three, ~3x fewer instructions per element
+// ---------------------------------------------------------------------------------------------
+// A velocity dispersion in km/s lives in a narrow window of the float range: every value in [2^-10, 2^22)
+// has its top 16 bits (sign 0, exponent, 7 mantissa bits) inside a run of 4096 consecutive prefixes.  So ONE
+// histogram of 4096 bins resolves 16 bits at once (the general kernel above spends a pass on 12), and the
+// bins that hold the ten target ranks are so thin (0.8 % wide: ~10^3 of 10^5 values each) that the second
+// read can simply COLLECT their members into shared memory, where two 8-bit steps per target finish the
+// selection.  Exact order statistics as before (the same ranks, NumPy's interpolation rule), bit-equal results.
+//   pass A  16-bit-prefix histogram + fp64 sum + maximum + the `bin`-wide histogram for the mode;
+//           block-wide exclusive scan of the histogram, one binary search per target rank;
+//   pass B  a byte table maps a prefix to its candidate list (or -1: 1 load + 1 compare per element);
+//           then one warp per target: two 256-bin histograms over its list.
+// One block of 1024 threads per row and ONE block per SM (110 KB of shared memory): 148 rows = 59 MB are in
+// flight at a time, so the second read of a row finds it in the 126 MB L2 -- a row crosses the HBM interface
+// once.  Rows this form cannot take -- a target rank among values outside the window (zeros, denormals,
+// > 4e6 km/s), NaNs, more candidates than the list holds -- are flagged in `todo` and done by the general
+// kernel, which is launched right behind and returns at once for every other row.
+#define FS_THREADS 1024
+#define FS_BINS 4096
+#define FS_LO16 (117u << 7)                 // bits >> 16 of 2^-10
+#define FS_CAND_MAX 16384
+#define FS_MODE_BINS (STATS_MODE_BINS_MAX + 1)
+#define FS_SMEM_BYTES ((FS_BINS + FS_MODE_BINS + FS_CAND_MAX + STATS_TARGETS * 256) * 4 + FS_BINS)
+
+__global__ void __launch_bounds__(FS_THREADS, 1) point_stats_fast_kernel(StatsArgs a) {
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    unsigned int* hist = reinterpret_cast<unsigned int*>(fs_smem);                 // [4096] 16-bit prefixes
+    unsigned int* mode_hist = hist + FS_BINS;                                      // [4097]
+    unsigned int* cand = mode_hist + FS_MODE_BINS;                                 // [16384]; first the scan of hist
+    unsigned int* sub = cand + FS_CAND_MAX;                                        // [10][256]
+    signed char* table = reinterpret_cast<signed char*>(sub + STATS_TARGETS * 256);   // prefix -> list / -1
+    __shared__ double red[FS_THREADS / 32];
+    __shared__ unsigned int warp_tot[FS_THREADS / 32];
+    __shared__ unsigned int rank[STATS_TARGETS], tbin[STATS_TARGETS], value_bits[STATS_TARGETS];
+    __shared__ int grp[STATS_TARGETS];
+    __shared__ unsigned int seg_off[STATS_TARGETS], seg_cnt[STATS_TARGETS], seg_fill[STATS_TARGETS];
+    __shared__ unsigned int max_bits, n_below, n_above;
+    __shared__ int give_up;
+
+    const int64_t n = a.n_real;
+    const float* __restrict__ sig = a.sigma + (size_t)blockIdx.x * a.sigma_stride;
+    rvmc_point_stats* st = a.stats_out + blockIdx.x;
+    const double qs[5] = {5.0, 16.0, 50.0, 84.0, 95.0};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x < STATS_TARGETS) {
+        const int t = threadIdx.x;
+        const double pos = (qs[t >> 1] / 100.0) * (double)(n - 1);
+        const int64_t lo = (int64_t)floor(pos);
+        rank[t] = (unsigned int)((t & 1) ? min(lo + 1, n - 1) : lo);
+        seg_fill[t] = 0;
+    }
+    if (threadIdx.x == 0) {
+        max_bits = 0;
+        n_below = 0;
+        n_above = 0;
+        give_up = 0;
+    }
+    for (int i = threadIdx.x; i < FS_BINS; i += FS_THREADS) {
+        hist[i] = 0;
+        table[i] = -1;
+    }
+    for (int i = threadIdx.x; i < FS_MODE_BINS; i += FS_THREADS) mode_hist[i] = 0;
+    for (int i = threadIdx.x; i < STATS_TARGETS * 256; i += FS_THREADS) sub[i] = 0;
+    __syncthreads();
+
+    // 16-byte loads, two in flight per thread; scalar head/tail for rows that do not start on 16 bytes
+    const int head = (int)min((int64_t)(((16u - (unsigned int)((uintptr_t)sig & 15u)) & 15u) >> 2), n);
+    const float4* __restrict__ sig4 = reinterpret_cast<const float4*>(sig + head);
+    const int64_t n4 = (n - head) >> 2;
+    const int64_t tail0 = head + 4 * n4;
+    auto for_each = [&](auto visit) {
+        if (threadIdx.x < head) visit(__ldg(sig + threadIdx.x));
+        int64_t j = threadIdx.x;
+        for (; j + FS_THREADS < n4; j += 2 * FS_THREADS) {
+            const float4 u = __ldg(sig4 + j), v = __ldg(sig4 + j + FS_THREADS);
+            visit(u.x); visit(u.y); visit(u.z); visit(u.w);
+            visit(v.x); visit(v.y); visit(v.z); visit(v.w);
+        }
+        if (j < n4) {
+            const float4 u = __ldg(sig4 + j);
+            visit(u.x); visit(u.y); visit(u.z); visit(u.w);
+        }
+        if (tail0 + threadIdx.x < n) visit(__ldg(sig + tail0 + threadIdx.x));
+    };
+
+    // ---- pass A ------------------------------------------------------------------------------------------
+    double sum = 0.0;
+    {
+        unsigned int mx = 0, below = 0, above = 0;
+        const float inv_bin = (float)(1.0 / a.bin);
+        int bin_exp;
+        const bool pow2_bin = frexp(a.bin, &bin_exp) == 0.5 && bin_exp > -100 && bin_exp < 100;
+        auto common = [&](float x, unsigned int bits) {
+            const unsigned int w = (bits >> 16) - FS_LO16;
+            if (w < FS_BINS) atomicAdd(&hist[w], 1u);
+            else if (bits < (FS_LO16 << 16)) ++below;
+            else ++above;
+            sum += (double)x;
+            mx = max(mx, bits);
+        };
+        if (pow2_bin) {
+            // x / bin is exact in fp32 for a power-of-two bin (the reference's 0.5): floor is the bin
+            for_each([&](float x) {
+                const unsigned int bits = __float_as_uint(x);
+                common(x, bits);
+                atomicAdd(&mode_hist[min((int)(x * inv_bin), STATS_MODE_BINS_MAX)], 1u);
+            });
+        } else {
+            for_each([&](float x) {
+                const unsigned int bits = __float_as_uint(x);
+                common(x, bits);
+                // edges are k*bin (np.arange(0, max+bin, bin)): fp32 guess, exact fp64 correction
+                const double xd = (double)x;
+                int k = (int)(x * inv_bin);
+                if ((double)k * a.bin > xd) --k;
+                else if ((double)(k + 1) * a.bin <= xd) ++k;
+                atomicAdd(&mode_hist[min(max(k, 0), STATS_MODE_BINS_MAX)], 1u);
+            });
+        }
+        atomicMax(&max_bits, mx);
+        for (int off = 16; off > 0; off >>= 1) {
+            below += __shfl_xor_sync(0xffffffffu, below, off);
+            above += __shfl_xor_sync(0xffffffffu, above, off);
+        }
+        if (lane == 0) {
+            if (below) atomicAdd(&n_below, below);
+            if (above) atomicAdd(&n_above, above);
+        }
+    }
+    sum = block_sum_f64(sum, red);       // contains the barriers
+    const double smax = (double)__uint_as_float(max_bits);
+    const double nbd = ceil((smax + a.bin) / a.bin) - 1.0;           // len(np.arange(0, max+bin, bin)) - 1
+    const int nb_mode = (nbd >= 1.0) ? (nbd < 2.0e9 ? (int)nbd : 2000000000) : 0;
+
+    // exclusive scan of the prefix histogram -> cand[0..4096): 4 bins per thread, warp scan, warp totals
+    {
+        const int b0 = threadIdx.x * 4;
+        const unsigned int c0 = hist[b0], c1 = hist[b0 + 1], c2 = hist[b0 + 2], c3 = hist[b0 + 3];
+        const unsigned int mine = c0 + c1 + c2 + c3;
+        unsigned int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned int wt = warp_tot[lane];
+            unsigned int winc = wt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, winc, off);
+                if (lane >= off) winc += t;
+            }
+            warp_tot[lane] = winc - wt;          // exclusive offset of each warp
+        }
+        __syncthreads();
+        const unsigned int ex = warp_tot[warp] + incl - mine;
+        cand[b0] = ex;
+        cand[b0 + 1] = ex + c0;
+        cand[b0 + 2] = ex + c0 + c1;
+        cand[b0 + 3] = ex + c0 + c1 + c2;
+    }
+    __syncthreads();
+    // one binary search per target rank: the last bin whose exclusive count is <= r
+    if (threadIdx.x < STATS_TARGETS) {
+        const int t = threadIdx.x;
+        const unsigned int r = rank[t];
+        const bool nan_present = max_bits > 0x7f800000u;
+        if (nan_present || r < n_below || (int64_t)r >= n - (int64_t)n_above) {
+            give_up = 1;
+        } else {
+            const unsigned int rr = r - n_below;
+            int lo = 0, hi = FS_BINS - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (cand[mid] <= rr) lo = mid;
+                else hi = mid - 1;
+            }
+            RVMC_DEV_ASSERT(hist[lo] > 0 && rr - cand[lo] < hist[lo]);
+            tbin[t] = (unsigned int)lo;
+            rank[t] = rr - cand[lo];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !give_up) {
+        int ng = 0;
+        unsigned int total = 0;
+        for (int t = 0; t < STATS_TARGETS; ++t) {
+            const unsigned int b = tbin[t];
+            if (table[b] < 0) {
+                table[b] = (signed char)ng;
+                seg_off[ng] = total;
+                seg_cnt[ng] = hist[b];
+                total += hist[b];
+                ++ng;
+            }
+            grp[t] = table[b];
+        }
+        if (total > FS_CAND_MAX) give_up = 1;
+    }
+    __syncthreads();
+    if (give_up) {                           // block-uniform: the general kernel takes this row
+        if (threadIdx.x == 0) a.todo[blockIdx.x] = 1;
+        return;
+    }
+
+    // ---- pass B: collect the members of the target bins ----------------------------------------------------
+    for_each([&](float x) {
+        const unsigned int bits = __float_as_uint(x);
+        const unsigned int w = (bits >> 16) - FS_LO16;
+        if (w < FS_BINS) {
+            const int g = table[w];
+            if (g >= 0) {
+                const unsigned int pos = atomicAdd(&seg_fill[g], 1u);
+                RVMC_DEV_ASSERT(pos < seg_cnt[g]);
+                cand[seg_off[g] + pos] = bits;
+            }
+        }
+    });
+    __syncthreads();
+    // one warp per target: two 8-bit steps over its list (the order inside a list does not matter)
+    if (warp < STATS_TARGETS) {
+        const int t = warp, g = grp[t];
+        const unsigned int* list = cand + seg_off[g];
+        const unsigned int m = seg_cnt[g];
+        unsigned int* h = sub + t * 256;
+        unsigned int r = rank[t];
+        for (unsigned int i = lane; i < m; i += 32) atomicAdd(&h[(list[i] >> 8) & 255u], 1u);
+        __syncwarp();
+        const unsigned int d1 = locate_digit(h, 256, r);
+        __syncwarp();
+        for (int i = lane; i < 256; i += 32) h[i] = 0;
+        __syncwarp();
+        for (unsigned int i = lane; i < m; i += 32) {
+            const unsigned int v = list[i];
+            if (((v >> 8) & 255u) == d1) atomicAdd(&h[v & 255u], 1u);
+        }
+        __syncwarp();
+        const unsigned int d0 = locate_digit(h, 256, r);
+        if (lane == 0) value_bits[t] = ((tbin[t] + FS_LO16) << 16) | (d1 << 8) | d0;
+    }
+    // the closed right end of the last bin (np.histogram): a value equal to the last edge counts in the last bin
+    if (threadIdx.x == 0 && nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX) {
+        mode_hist[nb_mode - 1] += mode_hist[nb_mode];
+        mode_hist[nb_mode] = 0;
+    }
+    __syncthreads();
+
+    // mode: first maximal bin (findBestDistributions.py:49-52), as in the general kernel
+    int mode_arg = 0;
+    if (threadIdx.x < 32 && nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX) {
+        unsigned int best = 0;
+        int arg = 0x7fffffff;
+        for (int k = threadIdx.x; k < nb_mode; k += 32) {
+            const unsigned int c = mode_hist[k];
+            if (c > best) {
+                best = c;
+                arg = k;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned int ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+            if (ob > best || (ob == best && oa < arg)) {
+                best = ob;
+                arg = oa;
+            }
+        }
+        mode_arg = (best > 0) ? arg : 0;
+    }
+    if (threadIdx.x == 0) {
+        double pct[5];
+        for (int k = 0; k < 5; ++k) {
+            // NumPy's _lerp: a + (b-a)*t, evaluated from b when t >= 0.5
+            const double pos = (qs[k] / 100.0) * (double)(n - 1);
+            const double t = pos - floor(pos);
+            const double lo = (double)__uint_as_float(value_bits[2 * k]);
+            const double hi = (double)__uint_as_float(value_bits[2 * k + 1]);
+            const double diff = hi - lo;
+            pct[k] = (t >= 0.5) ? hi - diff * (1.0 - t) : lo + diff * t;
+        }
+        st->p05 = pct[0];
+        st->p16 = pct[1];
+        st->median = pct[2];
+        st->p84 = pct[3];
+        st->p95 = pct[4];
+        st->mean = sum / (double)n;
+        st->sigma_max = smax;
+        st->n_hist_bins = (uint32_t)nb_mode;
+        st->n_guard = a.fail ? a.fail[2 * blockIdx.x] : 0u;
+        st->n_nonconverged = a.fail ? a.fail[2 * blockIdx.x + 1] : 0u;
+        st->reserved = 0;
+        if (nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX) {
+            st->mode = (double)mode_arg * a.bin + a.bin / 2.0;
+        } else {
+            st->mode = nan("");
+            st->reserved = nb_mode > STATS_MODE_BINS_MAX ? 1 : 0;
+        }
+        a.todo[blockIdx.x] = 0;
+    }
+    if (a.hist_out) {
+        uint32_t* ho = a.hist_out + (size_t)blockIdx.x * a.hist_bins;
+        for (int k = threadIdx.x; k < a.hist_bins; k += blockDim.x)
+            ho[k] = (k < nb_mode && k < STATS_MODE_BINS_MAX) ? mode_hist[k] : 0u;
+    }
+}
+
+// Both statistics kernels behind one call: the fast form for every row, the general form for what it left.
+static int launch_point_stats(StatsArgs sa, int64_t rows, uint8_t* todo, cudaStream_t stream) {
+    const bool general_only = getenv("RVMC_STATS_GENERAL") != nullptr;       // A/B and tests (read per call)
+    sa.todo = nullptr;
+    if (!general_only && todo) {
+        sa.todo = todo;
+        point_stats_fast_kernel<<<(unsigned int)rows, FS_THREADS, FS_SMEM_BYTES, stream>>>(sa);
+        int rc = cuda_status(cudaGetLastError(), "point_stats_fast_kernel launch");
+        if (rc) return rc;
+    }
+    point_stats_kernel<<<(unsigned int)rows, STATS_THREADS, STATS_SMEM_BYTES, stream>>>(sa);
+    return cuda_status(cudaGetLastError(), "point_stats_kernel launch");
+}
+
+static int stats_kernels_setup() {
+    int rc = cuda_status(cudaFuncSetAttribute(point_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              STATS_SMEM_BYTES), "point_stats_kernel smem");
+    if (!rc) rc = cuda_status(cudaFuncSetAttribute(point_stats_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   FS_SMEM_BYTES), "point_stats_fast_kernel smem");
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static int make_fused_point(const rvmc_pop_params& p, uint64_t seed, FusedPoint* out) {
@@ -974,7 +1311,8 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     void* ws = nullptr;
     const size_t desc_bytes = sizeof(FusedPoint) * (size_t)n_points;
     const size_t fail_bytes = 2 * sizeof(uint32_t) * (size_t)n_points;
-    RVMC_CUDA(cudaMallocAsync(&ws, desc_bytes + fail_bytes, stream));
+    const size_t todo_bytes = (size_t)n_points;
+    RVMC_CUDA(cudaMallocAsync(&ws, desc_bytes + fail_bytes + todo_bytes, stream));
     // the copy from pageable memory has been staged by the time the call returns; `host` may die
     rc = cuda_status(cudaMemcpyAsync(ws, host.data(), desc_bytes, cudaMemcpyHostToDevice, stream),
                      "cudaMemcpyAsync(points)");
@@ -985,6 +1323,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     }
     const FusedPoint* d_points = (const FusedPoint*)ws;
     uint32_t* d_fail = (uint32_t*)((char*)ws + desc_bytes);
+    uint8_t* d_todo = (uint8_t*)ws + desc_bytes + fail_bytes;
 
     const int64_t tiles_per_point = (n_real + ts.R - 1) / ts.R;
     int64_t batch = rvmc_grid_scratch_slots(0) / 2;               // the scratch is used as two halves
@@ -996,8 +1335,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
     rc = cuda_status(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (!rc) rc = cuda_status(cudaFuncSetAttribute(point_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   STATS_SMEM_BYTES), "point_stats_kernel smem");
+    if (!rc) rc = stats_kernels_setup();
     if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
     for (int k = 0; k < 2 && !rc; ++k)
         rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
@@ -1024,8 +1362,7 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
         sa.stats_out = stats_out + p0;
         sa.hist_out = hist_out ? hist_out + (size_t)p0 * hist_bins : nullptr;
         sa.fail = d_fail + 2 * p0;
-        point_stats_kernel<<<(unsigned int)np, STATS_THREADS, STATS_SMEM_BYTES, side>>>(sa);
-        rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
+        rc = launch_point_stats(sa, np, d_todo + p0, side);
         if (!rc) rc = cuda_status(cudaEventRecord(ev_stats[half], side), "cudaEventRecord");
     }
     // the caller's stream continues only after every statistics kernel has finished
@@ -1090,7 +1427,8 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
     void* ws = nullptr;
     const size_t desc_bytes = sizeof(FusedPoint) * (size_t)n_points;
     const size_t fail_bytes = 2 * sizeof(uint32_t) * (size_t)n_points * (size_t)n_fbins;
-    RVMC_CUDA(cudaMallocAsync(&ws, desc_bytes + fail_bytes, stream));
+    const size_t todo_bytes = (size_t)n_points * (size_t)n_fbins;
+    RVMC_CUDA(cudaMallocAsync(&ws, desc_bytes + fail_bytes + todo_bytes, stream));
     rc = cuda_status(cudaMemcpyAsync(ws, host.data(), desc_bytes, cudaMemcpyHostToDevice, stream),
                      "cudaMemcpyAsync(points)");
     if (!rc) rc = cuda_status(cudaMemsetAsync((char*)ws + desc_bytes, 0, fail_bytes, stream), "cudaMemsetAsync");
@@ -1100,6 +1438,7 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
     }
     const FusedPoint* d_points = (const FusedPoint*)ws;
     uint32_t* d_fail = (uint32_t*)((char*)ws + desc_bytes);
+    uint8_t* d_todo = (uint8_t*)ws + desc_bytes + fail_bytes;
 
     const int S = sample_size;
     // Tile height: up to 3072 slots, and -- for the small clusters whose phase C runs one thread per
@@ -1130,8 +1469,7 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
     rc = cuda_status(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (!rc) rc = cuda_status(cudaFuncSetAttribute(point_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   STATS_SMEM_BYTES), "point_stats_kernel smem");
+    if (!rc) rc = stats_kernels_setup();
     if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
     for (int k = 0; k < 2 && !rc; ++k)
         rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
@@ -1188,8 +1526,7 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
         sa.stats_out = stats_out + p0 * n_fbins;
         sa.hist_out = hist_out ? hist_out + (size_t)p0 * n_fbins * hist_bins : nullptr;
         sa.fail = d_fail + 2 * p0 * n_fbins;
-        point_stats_kernel<<<(unsigned int)rows, STATS_THREADS, STATS_SMEM_BYTES, side>>>(sa);
-        rc = cuda_status(cudaGetLastError(), "point_stats_kernel launch");
+        rc = launch_point_stats(sa, rows, d_todo + p0 * n_fbins, side);
         if (!rc) rc = cuda_status(cudaEventRecord(ev_stats[half], side), "cudaEventRecord");
     }
     for (int k = 0; k < 2; ++k)

@@ -10,6 +10,13 @@ Differences a user can see (all additive):
     (from then on the host copy is authoritative, so in-place edits are honoured).
   * `subsample_fused()` runs the infinite-pool limit of `subsample()` with per-star values kept
     on chip (the fast path; `subsample()` itself keeps the reference's finite-pool semantics).
+
+One INTENTIONAL divergence: `subsample(weighted=True)` with a SCALAR `measured_errors`.  The reference
+(RVMC.py:263-268) then divides by `np.sum(weights)` of a scalar -- the weight itself, not the sum over the
+stars -- so its `rv_mean` is the SUM of the velocities and its result is sqrt(sum_j (v_j - sum_k v_k)^2), a
+number its own docstring calls meaningless ("Only meaningful if an array of measured errors is provided",
+RVMC.py:247).  Here a scalar error is what it means: equal weights, i.e. the ddof = 0 dispersion.  Pass the
+errors as an array to get the reference's weighted formula bit for bit (tests/test_oracle_golden.py).
 """
 import ctypes as C
 import warnings

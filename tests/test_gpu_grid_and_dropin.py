@@ -197,6 +197,47 @@ def test_grid_search_recovers_known_parameters():
     assert np.all(np.diff(med[:, 1, 3]) < 0) and np.all(np.diff(med[2, 1, :]) > 0)
 
 
+@pytest.mark.parametrize("bin", [0.5, 0.3, 2.0])
+def test_fast_statistics_kernel_equals_the_general_one_and_numpy(bin, monkeypatch):
+    """point_stats_fast_kernel (16-bit prefix histogram + candidate lists, two reads) against the general
+    three-pass kernel (RVMC_STATS_GENERAL=1) and NumPy on the same sigma arrays: identical order statistics,
+    mode and histogram; means equal to rounding.  Rows the fast form cannot take (all zeros: the ranks fall
+    outside its window) go through the general kernel inside the same call."""
+    pops = [_abi.PopParams.defaults(fbin=f, min_period=p) for f in (0.1, 0.7, 1.0) for p in (1.4, 300.0)]
+    pops.append(_abi.PopParams.defaults(fbin=0.0, sigma_dyn=0.0))               # all-zero sigma row
+    pops.append(_abi.PopParams.defaults(fbin=0.02, sigma_dyn=0.0))              # mostly zeros: low ranks outside the window
+    seeds = list(range(40, 40 + len(pops)))
+    errs = np.zeros(12)
+    errs_noisy = M17
+    for err, n_real in ((errs_noisy, 100003), (errs, 20000), (errs_noisy, 7)):
+        use = pops if err is errs else pops[:6]
+        monkeypatch.delenv("RVMC_STATS_GENERAL", raising=False)
+        fast = grid.run_points(use, seeds[:len(use)], err, 12, n_real, bin=bin, keep_sigma=True, keep_hist=True,
+                               hist_bins=1024, distributed=False)
+        monkeypatch.setenv("RVMC_STATS_GENERAL", "1")
+        gen = grid.run_points(use, seeds[:len(use)], err, 12, n_real, bin=bin, keep_sigma=True, keep_hist=True,
+                              hist_bins=1024, distributed=False)
+        monkeypatch.delenv("RVMC_STATS_GENERAL", raising=False)
+        np.testing.assert_array_equal(fast["sigma"], gen["sigma"])
+        for k in grid.STATS_DTYPE.names:
+            if k == "mean":
+                np.testing.assert_allclose(fast["stats"][k], gen["stats"][k], rtol=1e-13, atol=0)
+            else:
+                np.testing.assert_array_equal(fast["stats"][k], gen["stats"][k], err_msg=k)
+        np.testing.assert_array_equal(fast["hist"], gen["hist"])
+        for i in range(len(use)):
+            sig = fast["sigma"][i].astype(np.float64)
+            for q, k in ((5, "p05"), (16, "p16"), (50, "median"), (84, "p84"), (95, "p95")):
+                assert fast["stats"][k][i] == np.percentile(sig, q), (i, k)
+            if sig.max() > 0:
+                edges = np.arange(0, sig.max() + bin, bin)
+                cnt, _ = np.histogram(sig, bins=edges)
+                nb = len(edges) - 1
+                assert fast["stats"]["n_hist_bins"][i] == nb
+                np.testing.assert_array_equal(fast["hist"][i][:min(nb, 1024)], cnt[:1024])
+                assert fast["stats"]["mode"][i] == edges[int(np.argmax(cnt))] + bin / 2
+
+
 def test_grid_per_point_failure_counters_and_best_fit_ignores_nan():
     """rvmc_point_stats.n_guard / n_nonconverged are filled per point by the producer kernels (what
     scipy.optimize.newton reports per call, RVMC.py:177-180): with eccentricities up to 0.999 the fp64
@@ -284,6 +325,13 @@ def test_rvmc_subsample_statistics_vs_reference_model():
     gw = c.subsample(sample_size=12, measured_errors=M17, number_of_samples=30000, weighted=True)
     rvs = rng.choice(c.radial_velocities, (30000, 12)) + rng.normal(0, M17, (30000, 12))
     assert sps.ks_2samp(gw, orc.sigma1d_weighted(rvs, M17)).pvalue > 0.01
+    # weighted=True with a SCALAR error: documented divergence from RVMC.py:263-268, whose
+    # np.sum(scalar weight) makes rv_mean the SUM of the velocities -- here equal weights = the ddof 0 dispersion
+    gs = c.subsample(sample_size=12, measured_errors=1.2, number_of_samples=30000, weighted=True)
+    want0 = np.std(rng.choice(pool, (30000, 12)) + rng.normal(0, 1.2, (30000, 12)), axis=1, ddof=0)
+    assert sps.ks_2samp(gs, want0).pvalue > 0.01
+    ref_quirk = np.sqrt(((rvs.T - rvs.sum(axis=1)).T ** 2).sum(axis=1))      # what the reference computes there
+    assert np.median(ref_quirk) > 3 * np.median(gs)                           # ... is not a dispersion at all
     fused, cnt = c.subsample_fused(sample_size=12, measured_errors=1.2, number_of_samples=30000, return_counters=True)
     assert sps.ks_2samp(fused.astype(np.float64), want).pvalue > 1e-3
     assert abs(cnt["binary_rvs"] / (30000 * 12) - c.fbin) < 0.01 and cnt["nonconverged"] == 0
