@@ -363,9 +363,9 @@ def run_gpu_arm(args):
     # the outputs of the product path (BiasCorr.calculate_radial_velocities): Delta-RV per binary and the
     # detection flags, bit-packed (or one byte each with --flag-transfer bytes)
     nw = (ns + 31) // 32
-    det = dv.empty((nstars, ns), "uint8", dev) if args.flag_transfer == "bytes" else None
-    bits = dv.empty((nstars, nw), "int32", dev) if args.flag_transfer == "bits" else None
-    out_bytes = nstars * ns * 4 + (nstars * ns if det is not None else nstars * nw * 4)
+    det = dv.empty((nstars, ns), "uint8", dev) if args.flag_transfer in ("bytes", "hybrid") else None
+    bits = dv.empty((nstars, nw), "int32", dev) if args.flag_transfer in ("bits", "hybrid") else None
+    out_bytes = nstars * ns * 4 + (nstars * ns if det is not None else 0) + (nstars * nw * 4 if bits is not None else 0)
     cnt = dv.zeros((4,), "int64", dev)
     BiasCorr.flag_transfer = args.flag_transfer
 
@@ -402,7 +402,9 @@ def run_gpu_arm(args):
     # ---- e2e: the drop-in class with host inputs and the bool detection array back on the host ---------
     t_obs_host = [DAYS6.copy() for _ in range(nstars)]
     h2d = nstars * 6 * 8 + nstars * 6 * 4 + nstars * 4
-    d2h = nstars * ns if args.flag_transfer == "bytes" else nstars * nw * 4
+    share = BiasCorr.flag_hybrid_byte_share
+    d2h = {"bytes": nstars * ns, "bits": nstars * nw * 4,
+           "hybrid": int(share * nstars * ns + (1 - share) * nstars * nw * 4)}[args.flag_transfer]
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step(k, read_delta_rv=False):
@@ -621,9 +623,12 @@ def run_gpu_arm(args):
                 "data": "synthetic", "config": workload_config(world, nstars, ns, out_bytes), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "BiasCorr(...).calculate_radial_velocities(); get_detected_binaries()",
-                        "flag_transfer": args.flag_transfer + (" (bit-packed by the kernel, widened to NumPy bool on the "
-                                                               "host by rvmc_unpack_bits_host, %d threads)"
-                                                               % dv.host_threads() if args.flag_transfer == "bits" else ""),
+                        "flag_transfer": {"bytes": "bytes (one uint8 per binary by DMA)",
+                                          "bits": "bits (bit-packed by the kernel, widened to NumPy bool on the host by "
+                                                  "rvmc_unpack_bits_host, %d threads)" % dv.host_threads(),
+                                          "hybrid": "hybrid (%.0f %% of the flags as bytes by DMA while %d host threads "
+                                                    "widen the bit-packed rest)" % (100 * share, dv.host_threads())
+                                          }[args.flag_transfer],
                         "detected_fraction": frac_det,
                         "with_delta_rv": {"value": e2e_drv_value, "unit": UNIT, "steps": e2e_drv_steps,
                                           "d2h_bytes_per_step": d2h + nstars * ns * 4,
@@ -663,8 +668,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--stars", type=int, default=100)
     ap.add_argument("--samples", type=int, default=10 ** 6)
-    ap.add_argument("--flag-transfer", default=os.environ.get("RVMC_FLAG_TRANSFER", "bits"), choices=["bits", "bytes"],
-                    help="how the detection flags reach the host: bit-packed + host unpack (default) or uint8")
+    ap.add_argument("--flag-transfer", default=os.environ.get("RVMC_FLAG_TRANSFER", "bits"), choices=["bits", "bytes", "hybrid"],
+                    help="how the detection flags reach the host: bit-packed + host unpack (default), uint8, or both routes at once")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipe-peaks", action="store_true")
     ap.add_argument("--no-grid", action="store_true", help="skip the grid-points/s legs (C5)")

@@ -230,6 +230,65 @@ def unpack_bits_overlapped(bits, n_cols, chunks, threads=None):
     return out.numpy().view(np.bool_)
 
 
+def fetch_flags_hybrid(det, bits, chunks, byte_share, threads=None):
+    """The detection flags of a pass whose kernels wrote BOTH forms (det: uint8 [nrows, ncols], bits: packed
+    words) -> NumPy bool [nrows, ncols], using the two routes into host memory AT THE SAME TIME: about
+    `byte_share` of the flags come as bytes by DMA straight into the result (the copy engines' path:
+    PCIe / IOMMU bound), the rest come bit-packed and are widened by the CPU threads (the host memory
+    system's path).  With several ranks on one host each route has its own ceiling (measured on an
+    8 x B200, 32-vCPU box: 120 GB/s of DMA writes in aggregate, ~200 GB/s of CPU streaming stores), and a
+    pass that must leave 100 MB of flags per rank in host memory every 3 ms needs both.  Blocks are assigned
+    to a route by error diffusion over their sizes, so the two routes stay busy side by side."""
+    t = torch()
+    lib = _abi.lib()
+    threads = host_threads() if threads is None else int(threads)
+    nrows, ncols = det.shape
+    nwords = bits.shape[1]
+    dev = det.device
+    if chunks is None:
+        ev = t.cuda.Event()
+        ev.record(t.cuda.current_stream(dev))
+        chunks = [(0, nrows, 0, ncols, ev)]
+    cs_bytes = _copy_stream(dev)
+    key = (dev.type, dev.index, "bits")
+    if key not in _copy_streams:
+        _copy_streams[key] = t.cuda.Stream(device=dev)
+    cs_bits = _copy_streams[key]
+    out = _host_result((nrows, ncols), t.uint8)
+    packed = t.empty(bits.shape, dtype=bits.dtype, pin_memory=True)
+    acc, plan = 0.0, []
+    for r0, r1, c0, c1, ev in chunks:
+        size = (r1 - r0) * (c1 - c0)
+        acc += byte_share * size
+        as_bytes = acc >= 0.5 * size
+        if as_bytes:
+            acc -= size
+        plan.append(as_bytes)
+    done = []
+    for (r0, r1, c0, c1, ev), as_bytes in zip(chunks, plan):
+        if as_bytes:
+            with t.cuda.stream(cs_bytes):
+                cs_bytes.wait_event(ev)
+                _copy_block(out, det, r0, r1, c0, c1)
+            done.append(None)
+        else:
+            with t.cuda.stream(cs_bits):
+                cs_bits.wait_event(ev)
+                _copy_block(packed, bits, r0, r1, c0 // 32, (c1 + 31) // 32)
+                e = t.cuda.Event()
+                e.record(cs_bits)
+            done.append(e)
+    p_ptr, o_ptr = packed.data_ptr(), out.data_ptr()
+    for (r0, r1, c0, c1, _), e in zip(chunks, done):
+        if e is None:
+            continue
+        e.synchronize()
+        _abi.check(lib.rvmc_unpack_bits_host(p_ptr + 4 * (r0 * nwords + c0 // 32), nwords, r1 - r0, c1 - c0,
+                                             o_ptr + r0 * ncols + c0, ncols, threads))
+    cs_bytes.synchronize()
+    return out.numpy().view(np.bool_)
+
+
 def soa(**tensors):
     """rvmc_orbit_soa from keyword tensors (missing = NULL)."""
     s = _abi.OrbitSoA()

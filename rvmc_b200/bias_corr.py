@@ -50,7 +50,9 @@ class BiasCorr(dv.LazyArrays):
     # how the detection flags of a fused pass travel to the host: "bits" = bit-packed by the kernel
     # (one __ballot_sync word per warp, 1/8 of the PCIe bytes) and widened to NumPy bool on the host by
     # the library's threaded helper; "bytes" = one uint8 per binary copied as is
+    # "hybrid" = both at once: a share of the ranges as bytes by DMA while the CPU widens the packed rest
     flag_transfer = os.environ.get("RVMC_FLAG_TRANSFER", "bits")
+    flag_hybrid_byte_share = float(os.environ.get("RVMC_FLAG_BYTE_SHARE", "0.4"))
 
     def __init__(self, t_obs, masses=None, mass_errors=None, number_of_samples=10**4, min_mass=6,
                  max_mass=20, min_period=10**0.15, max_period=10**3.5, period_pi=-0.5, mass_ratio_kappa=0,
@@ -488,9 +490,9 @@ class BiasCorr(dv.LazyArrays):
         drv = dv.empty((nstars, ns), "float32", dev)
         det = bits = None
         if d_err is not None:
-            if self.flag_transfer == "bits":
+            if self.flag_transfer in ("bits", "hybrid"):
                 bits = dv.empty((nstars, (ns + 31) // 32), "int32", dev)
-            else:
+            if self.flag_transfer in ("bytes", "hybrid"):
                 det = dv.empty((nstars, ns), "uint8", dev)
         counters = dv.zeros((4,), "int64", dev)
         per_star = dv.zeros((max(nstars, 1),), "int32", dev)
@@ -705,9 +707,9 @@ class BiasCorr(dv.LazyArrays):
             return dv.to_host(det).view(np.bool_)
         if key not in c["det"]:
             det = bits = None
-            if self.flag_transfer == "bits":
+            if self.flag_transfer in ("bits", "hybrid"):
                 bits = dv.empty((nstars, (ns + 31) // 32), "int32", dev)
-            else:
+            if self.flag_transfer in ("bytes", "hybrid"):
                 det = dv.empty((nstars, ns), "uint8", dev)
             self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], delta_RV, n_sigma_RV, None,
                                det, None, None, None, bits=bits, pop=c["pop"])
@@ -715,6 +717,8 @@ class BiasCorr(dv.LazyArrays):
         det, bits, chunks = c["det"][key]
         if chunks is not None and len(chunks) < 2:
             chunks = None
+        if bits is not None and det is not None:
+            return dv.fetch_flags_hybrid(det, bits, chunks, self.flag_hybrid_byte_share)
         if bits is not None:
             return dv.unpack_bits_overlapped(bits, ns, chunks)
         if chunks:

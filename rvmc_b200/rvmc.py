@@ -379,26 +379,26 @@ class RVMC(dv.LazyArrays):
 
 
 def plot_sigma_1d(sigma1d, labels, colors=None, hide_median=False):
-    """Histogram of velocity-dispersion distributions (RVMC.py:331-365)."""
+    """Step histograms of several sigma_1D distributions on one axis, medians dashed (the figure of
+    RVMC.py:331-365).  Plotting is outside the GPU path: this only hands the arrays to matplotlib and returns
+    (fig, ax), or None after the reference's two complaints (more than ten curves without colours; label count)."""
     import matplotlib.pyplot as plt
-    if colors is None:
-        colors = plt.rcParams['axes.prop_cycle'].by_key()['color']
-        if len(sigma1d) > 10:
-            print("Please specify your own colors if more than 10 distributions are to be plotted")
-            return
-    if len(labels) != len(sigma1d):
+    n = len(sigma1d)
+    if colors is None and n > 10:
+        print("Please specify your own colors if more than 10 distributions are to be plotted")
+        return None
+    if len(labels) != n:
         print("Warning! Number of labels does not match number of distributions")
-        return
-    fig, ax = plt.subplots(1, 1, figsize=(6, 5))
-    for i, dist in enumerate(sigma1d):
-        ax.hist(dist, histtype="step", bins=np.linspace(0, 100, 200), label=labels[i], density=True,
-                color=colors[i], lw=1.5)
-        if len(sigma1d) < 1000 and not hide_median:
-            ax.axvline(np.median(dist), color=colors[i], zorder=0.1, ls="--")
-    ax.set_xlabel(r"$\sigma_{\rm 1D}$ [km s$^{-1}$]")
-    ax.set_ylabel(r"Frequency [(km s$^{-1}$)$^{-1}$]")
-    if len(labels) <= 10:
+        return None
+    palette = list(colors) if colors is not None else plt.rcParams["axes.prop_cycle"].by_key()["color"]
+    edges = np.linspace(0, 100, 200)
+    fig, ax = plt.subplots(figsize=(6, 5))
+    for dist, label, colour in zip(sigma1d, labels, palette):
+        ax.hist(dist, bins=edges, density=True, histtype="step", lw=1.5, color=colour, label=label)
+        if not hide_median:
+            ax.axvline(np.median(dist), ls="--", color=colour, zorder=0.1)
+    ax.set(xlabel=r"$\sigma_{\rm 1D}$ [km s$^{-1}$]", ylabel=r"Frequency [(km s$^{-1}$)$^{-1}$]", xlim=(0, 50))
+    if n <= 10:
         ax.legend()
-    ax.set_xlim([0, 50])
-    plt.tight_layout()
+    fig.tight_layout()
     return fig, ax

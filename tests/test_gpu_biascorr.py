@@ -431,7 +431,7 @@ def test_biascorr_class_flag_transfer_modes_agree(transfer, monkeypatch):
     the same bool array; large enough that the pass is launched in overlapped ranges."""
     from rvmc_b200.bias_corr import BiasCorr
     res = {}
-    for mode in ("bits", "bytes"):
+    for mode in ("bits", "bytes", "hybrid"):
         monkeypatch.setattr(BiasCorr, "flag_transfer", mode)
         for shape in ((40, 110_000), (2, 2_100_000)):
             bc = BiasCorr([DAYS6] * shape[0], number_of_samples=shape[1], rv_errors=2.0, seed=5)
@@ -445,6 +445,7 @@ def test_biascorr_class_flag_transfer_modes_agree(transfer, monkeypatch):
             assert d2.shape == shape and d2.sum() < d.sum()
     for shape in ((40, 110_000), (2, 2_100_000)):
         np.testing.assert_array_equal(res[("bits", shape)], res[("bytes", shape)])
+        np.testing.assert_array_equal(res[("hybrid", shape)], res[("bytes", shape)])
 
 
 def test_editing_rv_errors_after_the_pass_changes_only_the_thresholds():
