@@ -16,6 +16,7 @@ METRICS = [
     ("launch__occupancy_limit_shared_mem", "occupancy limit (smem), blocks/SM"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("smsp__inst_executed.sum", "warp instructions executed"),
+    ("smsp__thread_inst_executed.sum", "thread instructions executed"),
     ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads / instruction"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "ISSUE SLOTS busy % (1 inst/clk/SMSP peak)"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe (FP32 + IMAD) %"),
