@@ -407,8 +407,11 @@ def run_gpu_arm(args):
            "hybrid": int(share * nstars * ns + (1 - share) * nstars * nw * 4)}[args.flag_transfer]
     e2e_steps = max(3, min(args.steps, 10))
 
+    from rvmc_b200 import _trace
+
     def e2e_step(k, read_delta_rv=False):
-        bc = BiasCorr(t_obs_host, number_of_samples=ns, rv_errors=2.0, seed=1000 + k + 7919 * rank, device=dev)
+        with _trace.span("biascorr.construct"):
+            bc = BiasCorr(t_obs_host, number_of_samples=ns, rv_errors=2.0, seed=1000 + k + 7919 * rank, device=dev)
         bc.calculate_radial_velocities(delta_RV=20, n_sigma_RV=4)
         d = bc.get_detected_binaries(delta_RV=20, n_sigma_RV=4)
         if read_delta_rv:
@@ -429,6 +432,13 @@ def run_gpu_arm(args):
 
     e2e_s, frac_det = e2e_time(e2e_steps, False)
     e2e_value = world * units_per_step * e2e_steps / e2e_s
+    # where the host side of a step goes (rank 0): a second, traced run of the same steps -- host timers and NVTX
+    # ranges only, no extra synchronisation; not the timed run above
+    _trace.enable("1")
+    _trace.totals(reset=True)
+    e2e_time(e2e_steps, False)
+    e2e_phases = {k: round(1e3 * v[1] / (e2e_steps + 2), 3) for k, v in _trace.totals(reset=True).items()}
+    _trace.enable("")
     # what a user who also reads `.delta_rv` (RVMC_bias_corr.py:422) pays: 4 B per binary more over PCIe
     e2e_drv_steps = 3
     e2e_drv_s, _ = e2e_time(e2e_drv_steps, True)
@@ -630,6 +640,7 @@ def run_gpu_arm(args):
                                                     "widen the bit-packed rest)" % (100 * share, dv.host_threads())
                                           }[args.flag_transfer],
                         "detected_fraction": frac_det,
+                        "host_phases_ms_per_step_rank0": e2e_phases,
                         "with_delta_rv": {"value": e2e_drv_value, "unit": UNIT, "steps": e2e_drv_steps,
                                           "d2h_bytes_per_step": d2h + nstars * ns * 4,
                                           "api": "... plus reading bc.delta_rv (float32, 4 B per binary)"}},

@@ -465,7 +465,8 @@ class BiasCorr(dv.LazyArrays):
         the same pass and cached for `get_detected_binaries`."""
         dev = self._device
         nstars, ns = self.number_of_stars, int(self.number_of_samples)
-        nep, max_ep, d_nep, d_tobs, d_err = self._tables()
+        with span("biascorr.tables"):
+            nep, max_ep, d_nep, d_tobs, d_err = self._tables()
         self._rv_seed = self._next_seed()
         self._rv_user = None
         quirk = 0 if self.physical_phase else 1
@@ -524,7 +525,7 @@ class BiasCorr(dv.LazyArrays):
             ready = t.cuda.Event()
             ready.record(main)
             streams[1].wait_event(ready)
-        with dv.DeviceGuard(dev):
+        with dv.DeviceGuard(dev), span("biascorr.launch_ranges"):
             for k, (s0, s1, c0, c1) in enumerate(ranges):
                 st = streams[k % len(streams)]
                 launch(s0, s1, C.c_void_p(st.cuda_stream), c0, c1)
@@ -720,7 +721,8 @@ class BiasCorr(dv.LazyArrays):
         if bits is not None and det is not None:
             return dv.fetch_flags_hybrid(det, bits, chunks, self.flag_hybrid_byte_share)
         if bits is not None:
-            return dv.unpack_bits_overlapped(bits, ns, chunks)
+            with span("biascorr.fetch_flags"):
+                return dv.unpack_bits_overlapped(bits, ns, chunks)
         if chunks:
             return dv.to_host_overlapped(det, chunks).view(np.bool_)
         return dv.to_host(det).view(np.bool_)

@@ -58,6 +58,16 @@ static DeviceState* current_state(int* rc_out) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         s.sms = sms;
         s.checked = (major == 10 && minor == 0) ? 1 : -1;
+        if (s.checked > 0) {
+            // the stream-ordered allocations of the grid entries (descriptors, counters: ~1 MB per call) stay
+            // in the device's default pool between calls instead of going back to the driver at every sync
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+                unsigned long long keep = 64ull << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        }
         if (s.checked < 0)
             set_error("device %d is sm_%d%d; the kernels are built for sm_100a only and there is no "
                       "fallback path", dev, major, minor);

@@ -1097,6 +1097,37 @@ static int launch_point_stats(StatsArgs sa, int64_t rows, uint8_t* todo, cudaStr
     return cuda_status(cudaGetLastError(), "point_stats_kernel launch");
 }
 
+// Per host thread and device: the side stream the statistics kernels run on and the three events that
+// order it against the caller's stream, created once and reused by every grid call of the thread (a grid
+// fit makes many calls; creating and destroying them costs more than a batch of a small grid), and the
+// one-time opt-in of the two statistics kernels to > 48 KB of shared memory.
+struct GridAux {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
+};
+static int stats_kernels_setup();
+static int grid_aux(GridAux** out) {
+    static thread_local std::vector<GridAux> per_device;
+    int dev = 0;
+    int rc = cuda_status(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    if ((int)per_device.size() <= dev) per_device.resize(dev + 1);
+    GridAux& a = per_device[dev];
+    if (!a.side) {
+        rc = stats_kernels_setup();
+        if (!rc) rc = cuda_status(cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&a.ev_fused, cudaEventDisableTiming), "cudaEventCreate");
+        for (int k = 0; k < 2 && !rc; ++k)
+            rc = cuda_status(cudaEventCreateWithFlags(&a.ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
+        if (rc) {
+            a.side = nullptr;        // try again on the next call
+            return rc;
+        }
+    }
+    *out = &a;
+    return RVMC_OK;
+}
+
 static int stats_kernels_setup() {
     int rc = cuda_status(cudaFuncSetAttribute(point_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               STATS_SMEM_BYTES), "point_stats_kernel smem");
@@ -1332,13 +1363,14 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
     // The statistics kernel of batch b runs on a side stream while the fused kernel of batch b+1
     // runs on the caller's stream (scratch halves alternate), so its latency-bound passes hide
     // behind the compute-bound Monte Carlo.
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
-    rc = cuda_status(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (!rc) rc = stats_kernels_setup();
-    if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
-    for (int k = 0; k < 2 && !rc; ++k)
-        rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
+    GridAux* aux = nullptr;
+    rc = grid_aux(&aux);
+    if (rc) {
+        cudaFreeAsync(ws, stream);
+        return rc;
+    }
+    cudaStream_t side = aux->side;
+    cudaEvent_t ev_fused = aux->ev_fused, *ev_stats = aux->ev_stats;
     int64_t nb = 0;
     for (int64_t p0 = 0; p0 < n_points && !rc; p0 += batch, ++nb) {
         const int64_t np = (n_points - p0 < batch) ? n_points - p0 : batch;
@@ -1371,10 +1403,6 @@ int rvmc_grid_run(const rvmc_grid_point* points, int64_t n_points, const float* 
             int rc2 = cuda_status(cudaStreamWaitEvent(stream, ev_stats[k], 0), "cudaStreamWaitEvent");
             if (!rc) rc = rc2;
         }
-    if (ev_fused) cudaEventDestroy(ev_fused);
-    for (int k = 0; k < 2; ++k)
-        if (ev_stats[k]) cudaEventDestroy(ev_stats[k]);
-    if (side) cudaStreamDestroy(side);       // deferred by the runtime until its work has drained
     cudaFreeAsync(ws, stream);
     return rc;
 }
@@ -1466,13 +1494,14 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
         return RVMC_ERR_UNSUPPORTED;
     }
     const bool fast = iters1 && !guard;
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fused = nullptr, ev_stats[2] = {nullptr, nullptr};
-    rc = cuda_status(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (!rc) rc = stats_kernels_setup();
-    if (!rc) rc = cuda_status(cudaEventCreateWithFlags(&ev_fused, cudaEventDisableTiming), "cudaEventCreate");
-    for (int k = 0; k < 2 && !rc; ++k)
-        rc = cuda_status(cudaEventCreateWithFlags(&ev_stats[k], cudaEventDisableTiming), "cudaEventCreate");
+    GridAux* aux = nullptr;
+    rc = grid_aux(&aux);
+    if (rc) {
+        cudaFreeAsync(ws, stream);
+        return rc;
+    }
+    cudaStream_t side = aux->side;
+    cudaEvent_t ev_fused = aux->ev_fused, *ev_stats = aux->ev_stats;
     auto launch_fbins = [&](auto kernel, unsigned int total) -> int {
         if (smem > 48 * 1024) {
             int rc2 = cuda_status(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -1534,10 +1563,6 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
             int rc2 = cuda_status(cudaStreamWaitEvent(stream, ev_stats[k], 0), "cudaStreamWaitEvent");
             if (!rc) rc = rc2;
         }
-    if (ev_fused) cudaEventDestroy(ev_fused);
-    for (int k = 0; k < 2; ++k)
-        if (ev_stats[k]) cudaEventDestroy(ev_stats[k]);
-    if (side) cudaStreamDestroy(side);
     cudaFreeAsync(ws, stream);
     return rc;
 }
