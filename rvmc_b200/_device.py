@@ -180,8 +180,7 @@ def to_host_overlapped(tensor, chunks):
 
 def host_threads():
     """Threads the host-side helpers of the library may use in this process: RVMC_HOST_THREADS, else the
-    half of the cores this process may run on divided by the ranks sharing the node (LOCAL_WORLD_SIZE),
-    at most 8."""
+    cores this process may run on divided by the ranks sharing the node (LOCAL_WORLD_SIZE), at most 8."""
     import os
     env = os.environ.get("RVMC_HOST_THREADS")
     if env:
@@ -191,10 +190,11 @@ def host_threads():
     except AttributeError:          # pragma: no cover
         cores = os.cpu_count() or 1
     local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    # half the rank's share of the cores: the widening is bound by the host's memory system long before
-    # that (measured on a 32-vCPU, 8-GPU box: 16 threads in total reach 220 GB/s, 32 threads 200 GB/s), and
-    # the other half stays free for the ranks' own Python threads
-    return max(1, min(8, cores // (2 * local_world)))
+    # the rank's share of the cores.  The widening is bound by the host's memory system long before that
+    # (32-vCPU, 8-GPU box: 16 threads in total stream 205 GB/s, 32 threads 203 GB/s), but inside the real
+    # pass, where the helper threads also sleep between blocks, 4 per rank measured best (8.6e11 against
+    # 7.6e11 RV/s with 2)
+    return max(1, min(8, cores // local_world))
 
 
 def unpack_bits_overlapped(bits, n_cols, chunks, threads=None):
