@@ -9,7 +9,8 @@ other BASELINE config (C1 example cluster, C3 six data_sana variants, C4 data_RT
 
 A step = one pass of the hot path (rvmc_biascorr_fused_packed: sample + Kepler + RV at 6 epochs + noise +
 Delta-RV + significance test) over 10^8 binaries per GPU, writing Delta-RV (fp32) and the detection
-flags (bit-packed) for every binary to HBM -- the outputs of the product path.  `value` is timed with
+flags (bit-packed when ranks share a host, one byte each for a single rank: --flag-transfer auto) for every
+binary to HBM -- the outputs of the product path.  `value` is timed with
 CUDA events on the launching stream with everything resident on the device; `e2e` is the same metric
 through the drop-in Python class (`BiasCorr(...)` -> `calculate_radial_velocities()` ->
 `get_detected_binaries()`) with host inputs and the bool detection array back in host memory inside the
@@ -362,12 +363,14 @@ def run_gpu_arm(args):
     drv = dv.empty((nstars, ns), "float32", dev)
     # the outputs of the product path (BiasCorr.calculate_radial_velocities): Delta-RV per binary and the
     # detection flags, bit-packed (or one byte each with --flag-transfer bytes)
+    BiasCorr.flag_transfer = args.flag_transfer
+    if args.flag_transfer == "auto":          # what the class resolves it to in this job
+        args.flag_transfer = "bits" if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1 else "bytes"
     nw = (ns + 31) // 32
     det = dv.empty((nstars, ns), "uint8", dev) if args.flag_transfer in ("bytes", "hybrid") else None
     bits = dv.empty((nstars, nw), "int32", dev) if args.flag_transfer in ("bits", "hybrid") else None
     out_bytes = nstars * ns * 4 + (nstars * ns if det is not None else 0) + (nstars * nw * 4 if bits is not None else 0)
     cnt = dv.zeros((4,), "int64", dev)
-    BiasCorr.flag_transfer = args.flag_transfer
 
     def step():
         _abi.check(lib.rvmc_biascorr_fused_packed(C.byref(p), seed, noise_seed, 0, nstars, 6, dv.ptr(d_nep),
@@ -522,7 +525,10 @@ def run_gpu_arm(args):
                                      % target,
                          "variants": c3, "binary_rvs_per_s": world * c3_total_rv / (c3_total_ms * 1e-3),
                          "unit": "binary RV/s", "timing": "CUDA events, mean of 2 launches after 1 warm-up, max over ranks",
-                         "_units_per_s_rank": c3_total_rv / (c3_total_ms * 1e-3)}
+                         # the roofline block uses the f_bin 0.7 variants: the executed count of the ncu capture is
+                         # per binary RV AT f_bin 0.7 (at lower fractions the single-star slots weigh more per binary)
+                         "_units_per_s_rank": sum(v["binary_rvs"] for v in c3 if v["fbin"] == 0.7) /
+                                              (1e-3 * sum(v["ms"] for v in c3 if v["fbin"] == 0.7))}
 
         # ---- C4: the ten data_RT20 clusters, weighted dispersion, 10^6 realizations each --------------------
         n_real4 = int(args.c4_realizations)
@@ -626,7 +632,8 @@ def run_gpu_arm(args):
                     4.0 / (12 * 0.7), peaks, peak_src, pipes)
                 configs[key]["roofline"]["note"] = (
                     "a unit is one binary RV; the kernel also draws the coin + noise of every SINGLE star slot, so the "
-                    "executed count per binary RV grows as f_bin falls (the ncu figure is for S = 12, f_bin 0.7)")
+                    "executed count per binary RV grows as f_bin falls (the ncu figure is for S = 12, f_bin 0.7; the C3 "
+                    "block is computed from the four f_bin 0.7 variants)")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 period/phase reduction)",
@@ -679,8 +686,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--stars", type=int, default=100)
     ap.add_argument("--samples", type=int, default=10 ** 6)
-    ap.add_argument("--flag-transfer", default=os.environ.get("RVMC_FLAG_TRANSFER", "bits"), choices=["bits", "bytes", "hybrid"],
-                    help="how the detection flags reach the host: bit-packed + host unpack (default), uint8, or both routes at once")
+    ap.add_argument("--flag-transfer", default=os.environ.get("RVMC_FLAG_TRANSFER", "auto"),
+                    choices=["auto", "bits", "bytes", "hybrid"],
+                    help="how the detection flags reach the host: auto (default: bytes for one rank per host, bit-packed + host "
+                         "unpack when ranks share the host), bits, bytes, or both routes at once")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipe-peaks", action="store_true")
     ap.add_argument("--no-grid", action="store_true", help="skip the grid-points/s legs (C5)")

@@ -50,8 +50,11 @@ class BiasCorr(dv.LazyArrays):
     # how the detection flags of a fused pass travel to the host: "bits" = bit-packed by the kernel
     # (one __ballot_sync word per warp, 1/8 of the PCIe bytes) and widened to NumPy bool on the host by
     # the library's threaded helper; "bytes" = one uint8 per binary copied as is
-    # "hybrid" = both at once: a share of the ranges as bytes by DMA while the CPU widens the packed rest
-    flag_transfer = os.environ.get("RVMC_FLAG_TRANSFER", "bits")
+    # "hybrid" = both at once: a share of the ranges as bytes by DMA while the CPU widens the packed rest;
+    # "auto" (default) = "bytes" for a rank that has the host to itself (one copy engine at 56 GB/s hides
+    # behind the kernel and costs no CPU), "bits" as soon as ranks share the host (LOCAL_WORLD_SIZE > 1: the
+    # DMA route of the whole box saturates at 121 GB/s, the widening route at 205 GB/s)
+    flag_transfer = os.environ.get("RVMC_FLAG_TRANSFER", "auto")
     flag_hybrid_byte_share = float(os.environ.get("RVMC_FLAG_BYTE_SHARE", "0.4"))
 
     def __init__(self, t_obs, masses=None, mass_errors=None, number_of_samples=10**4, min_mass=6,
@@ -491,9 +494,9 @@ class BiasCorr(dv.LazyArrays):
         drv = dv.empty((nstars, ns), "float32", dev)
         det = bits = None
         if d_err is not None:
-            if self.flag_transfer in ("bits", "hybrid"):
+            if self._flag_mode() in ("bits", "hybrid"):
                 bits = dv.empty((nstars, (ns + 31) // 32), "int32", dev)
-            if self.flag_transfer in ("bytes", "hybrid"):
+            if self._flag_mode() in ("bytes", "hybrid"):
                 det = dv.empty((nstars, ns), "uint8", dev)
         counters = dv.zeros((4,), "int64", dev)
         per_star = dv.zeros((max(nstars, 1),), "int32", dev)
@@ -599,6 +602,14 @@ class BiasCorr(dv.LazyArrays):
         with dv.DeviceGuard(self._device):
             self._fused_launcher(max_ep, d_nep, d_tobs, d_err, delta_RV, n_sigma_RV, drv, det, rv_out, counters,
                                  per_star, bits=bits, pop=pop)(int(s0), int(s1))
+
+    def _flag_mode(self):
+        mode = self.flag_transfer
+        if mode == "auto":
+            mode = "bits" if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1 else "bytes"
+        if mode not in ("bits", "bytes", "hybrid"):
+            raise ValueError("flag_transfer must be 'auto', 'bits', 'bytes' or 'hybrid' (got %r)" % (mode,))
+        return mode
 
     def _errors_fingerprint(self):
         """The measurement errors AS THEY ARE NOW.  get_detected_binaries() compares it with the one taken
@@ -708,9 +719,9 @@ class BiasCorr(dv.LazyArrays):
             return dv.to_host(det).view(np.bool_)
         if key not in c["det"]:
             det = bits = None
-            if self.flag_transfer in ("bits", "hybrid"):
+            if self._flag_mode() in ("bits", "hybrid"):
                 bits = dv.empty((nstars, (ns + 31) // 32), "int32", dev)
-            if self.flag_transfer in ("bytes", "hybrid"):
+            if self._flag_mode() in ("bytes", "hybrid"):
                 det = dv.empty((nstars, ns), "uint8", dev)
             self._launch_fused(c["nep"], c["max_ep"], c["d_nep"], c["d_tobs"], c["d_err"], delta_RV, n_sigma_RV, None,
                                det, None, None, None, bits=bits, pop=c["pop"])

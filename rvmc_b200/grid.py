@@ -704,12 +704,13 @@ def grid_search(axes, sample_size=12, measured_errors=M17_ERRORS, number_of_samp
         # findBestDistributions.py:138-158: first strict minimum below the initial distance of 100, in C
         # order; the strict `<` never selects a NaN (an all-zero sigma_1D distribution has no mode), so
         # NaNs are masked out rather than left to np.argmin, which would return the first of them
-        central = out["stats"]["mode" if usemode else "median"]
+        central = np.ascontiguousarray(out["stats"]["mode" if usemode else "median"])   # one strided gather of the field
         d = np.abs(central - observed_sigma)
         ok = d < 100                                   # False for NaN
         best, idx = 100.0, 0
         if ok.any():
-            idx = int(np.argmin(np.where(ok, d, np.inf)))          # first minimum in C order
+            d[~ok] = np.inf
+            idx = int(np.argmin(d))                    # first minimum in C order
             best = float(d.flat[idx])
         out["best_index"] = tuple(int(v) for v in np.unravel_index(idx, shape))
         out["best_params"] = {k: float(v[j]) for k, v, j in zip(names, vals, out["best_index"])}

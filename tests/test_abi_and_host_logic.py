@@ -297,3 +297,30 @@ def test_call_seeds_of_neighbouring_user_seeds_are_disjoint():
             assert v not in seen, (s, k, seen[v])
             seen[v] = (s, k)
     assert call_seed(5, 3) == call_seed(5 + 2 ** 64, 3)           # the seed is taken mod 2^64
+
+
+def test_trace_spans_are_free_when_off_and_recorded_when_on(caplog):
+    """rvmc_b200._trace (NVTX ranges + logging where the reference has bare prints): a span
+    costs nothing when tracing is off; when on it is timed, accumulated and logged at DEBUG level."""
+    import logging
+    import time
+
+    from rvmc_b200 import _trace
+    _trace.enable("")
+    _trace.totals(reset=True)
+    assert _trace.span("x") is _trace.span("y")              # one shared null context
+    with _trace.span("off"):
+        pass
+    assert _trace.totals() == {}
+    _trace.enable("1")
+    try:
+        with caplog.at_level(logging.DEBUG, logger="rvmc_b200"):
+            for _ in range(3):
+                with _trace.span("phase.a"):
+                    time.sleep(0.002)
+        tot = _trace.totals(reset=True)
+        assert tot["phase.a"][0] == 3 and 0.005 < tot["phase.a"][1] < 0.5
+        assert sum("phase.a" in r.getMessage() for r in caplog.records) == 3
+        assert _trace.totals() == {}
+    finally:
+        _trace.enable("")
