@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) biascorr_fused_kern
         o.wturn = u01_f32(wb.z);
         const float K = semi_amplitude_f32(a.P32, o);
         float sw, cw;
-        sincos_turn(o.wturn, sw, cw);
+        sincos_omega(o.wturn, sw, cw);
         const float Ksw = K * sw, Kcw = K * cw;
         const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
         const double c0 = quirk ? RVMC_TWO_PI * uphase : uphase;

@@ -226,7 +226,7 @@ RVMC_HD float orbit_rv_f32(const PopF32& P, const OrbitF32& o, int iters, float*
     const float K = semi_amplitude_f32(P, o);
     const float aphase = fabsf(o.phase);
     float sw, cw;
-    sincos_turn(o.wturn, sw, cw);
+    sincos_omega(o.wturn, sw, cw);
     const float rome2 = fast_sqrt((1.0f - o.e) * (1.0f + o.e));
     const float shape = kepler_shape_f32<ITERS, GUARD>(6.283185307179586f * aphase, RVMC_TWO_PI * (double)aphase,
                                          o.phase < 0.0f, o.e, rome2, sw, cw, iters, P.guard_amp, guard, bad);

@@ -133,6 +133,23 @@ RVMC_HD void sincos_turn(float t, float& s, float& c) {
     sincos_kernel(r, ss, cc);
     quadrant_fix((int)float_bits(kb), ss, cc, s, c);
 }
+// sin/cos of the orientation angle omega = 2 pi t, t a uniform draw in [0, 1): MUFU.SIN / MUFU.COS on the
+// angle folded into [-pi, pi) (t - 1 is exact for t >= 0.5) -- 5 instructions against 26 for the polynomial
+// pair.  The unit's absolute error there is < 5e-7 (+ 2e-7 from rounding 2 pi t), and the RV is LINEAR in
+// (sin omega, cos omega), so this costs < 1e-6 of K; measured on 1.2e6 orbits per population the largest
+// |RV - oracle| / max(|RV|, K) moves from 1.3-1.6e-6 to 1.3-1.8e-6 (tools/parity_margin.py), against a bound
+// of 1e-5, for +2 % on the multi-epoch kernel and +4 % on the fused sigma_1D kernels.  The eccentric anomaly
+// keeps its polynomial pair (periastron amplifies an error in E, not one in omega).  -DRVMC_OMEGA_POLY restores
+// the polynomial.
+RVMC_HD void sincos_omega(float t, float& s, float& c) {
+#if defined(__CUDA_ARCH__) && !defined(RVMC_OMEGA_POLY)
+    const float th = (t - (t >= 0.5f ? 1.0f : 0.0f)) * 6.283185307179586f;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
+#else
+    sincos_turn(t, s, c);
+#endif
+}
 // sin/cos of x radians for |x| up to a few pi (two-constant Cody-Waite reduction).
 RVMC_HD void sincos_rad(float x, float& s, float& c) {
     const float k = rintf(x * 0.6366197723675814f);

@@ -742,7 +742,8 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) point_stats_kernel(StatsArgs
             const double lo = (double)__uint_as_float(prefix[2 * k]);
             const double hi = (double)__uint_as_float(prefix[2 * k + 1]);
             const double diff = hi - lo;
-            pct[k] = (t >= 0.5) ? hi - diff * (1.0 - t) : lo + diff * t;
+            // separate roundings, as NumPy's ufuncs do: a contracted FMA differs in the last bit now and then
+            pct[k] = (t >= 0.5) ? __dsub_rn(hi, __dmul_rn(diff, 1.0 - t)) : __dadd_rn(lo, __dmul_rn(diff, t));
         }
         st->p05 = pct[0];
         st->p16 = pct[1];
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) point_stats_kernel(StatsArgs
         st->n_nonconverged = a.fail ? a.fail[2 * blockIdx.x + 1] : 0u;
         st->reserved = 0;
         if (nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX) {
-            st->mode = (double)mode_arg * a.bin + a.bin / 2.0;
+            st->mode = __dadd_rn(__dmul_rn((double)mode_arg, a.bin), a.bin / 2.0);    // bins[i] + width / 2, rounded like NumPy
         } else {
             // no bin at all (every sigma is 0: the reference's np.max of an empty histogram raises)
             // or more bins than the kernel's table holds (flagged)
@@ -1055,7 +1056,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) point_stats_fast_kernel(StatsAr
             const double lo = (double)__uint_as_float(value_bits[2 * k]);
             const double hi = (double)__uint_as_float(value_bits[2 * k + 1]);
             const double diff = hi - lo;
-            pct[k] = (t >= 0.5) ? hi - diff * (1.0 - t) : lo + diff * t;
+            // separate roundings, as NumPy's ufuncs do: a contracted FMA differs in the last bit now and then
+            pct[k] = (t >= 0.5) ? __dsub_rn(hi, __dmul_rn(diff, 1.0 - t)) : __dadd_rn(lo, __dmul_rn(diff, t));
         }
         st->p05 = pct[0];
         st->p16 = pct[1];
@@ -1069,7 +1071,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) point_stats_fast_kernel(StatsAr
         st->n_nonconverged = a.fail ? a.fail[2 * blockIdx.x + 1] : 0u;
         st->reserved = 0;
         if (nb_mode > 0 && nb_mode <= STATS_MODE_BINS_MAX) {
-            st->mode = (double)mode_arg * a.bin + a.bin / 2.0;
+            st->mode = __dadd_rn(__dmul_rn((double)mode_arg, a.bin), a.bin / 2.0);    // bins[i] + width / 2, rounded like NumPy
         } else {
             st->mode = nan("");
             st->reserved = nb_mode > STATS_MODE_BINS_MAX ? 1 : 0;

@@ -324,3 +324,34 @@ def test_trace_spans_are_free_when_off_and_recorded_when_on(caplog):
         assert _trace.totals() == {}
     finally:
         _trace.enable("")
+
+
+def test_flag_transfer_resolution_range_weights_and_host_threads(monkeypatch):
+    """Host policy of the end-to-end pass (no GPU needed): `auto` resolves to the byte route for a rank that
+    has the host to itself and to the packed route when ranks share it; the launch ranges are small at both
+    ends; the helper-thread count follows RVMC_HOST_THREADS / the rank's share of the cores."""
+    from rvmc_b200 import _device as dv
+    from rvmc_b200.bias_corr import BiasCorr
+    bc = BiasCorr.__new__(BiasCorr)                      # policy only: no device is touched
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    monkeypatch.setattr(BiasCorr, "flag_transfer", "auto")
+    assert bc._flag_mode() == "bytes"
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert bc._flag_mode() == "bits"
+    for mode in ("bits", "bytes", "hybrid"):
+        monkeypatch.setattr(BiasCorr, "flag_transfer", mode)
+        assert bc._flag_mode() == mode
+    monkeypatch.setattr(BiasCorr, "flag_transfer", "carrier pigeon")
+    with pytest.raises(ValueError):
+        bc._flag_mode()
+    w = BiasCorr._range_weights(12)
+    assert len(w) == 12 and np.allclose(w, w[::-1]) and w[0] == w.min() and w[0] / w.sum() < 0.03
+    assert np.all(np.diff(w[:6]) > 0) and np.all(np.diff(w[6:]) < 0)
+    assert np.allclose(BiasCorr._range_weights(1), [1.0])
+    monkeypatch.setenv("RVMC_HOST_THREADS", "5")
+    assert dv.host_threads() == 5
+    monkeypatch.delenv("RVMC_HOST_THREADS")
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1000")
+    assert dv.host_threads() == 1
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert 1 <= dv.host_threads() <= 8
