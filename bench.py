@@ -613,7 +613,9 @@ def run_gpu_arm(args):
         # ncu --set full capture (the results minus what still sits in the 126 MB L2 when the kernel ends)
         traffic, traffic_src = args.traffic_bytes, "--traffic-bytes"
         if traffic is None and (nstars, ns) == (100, 10 ** 6):
-            traffic, traffic_src = EXEC_MULTI.get("traffic_bytes"), EXEC_MULTI["source"]
+            traffic = EXEC_MULTI.get("traffic_bytes_packed_flags" if det is None else "traffic_bytes",
+                                     EXEC_MULTI.get("traffic_bytes"))
+            traffic_src = EXEC_MULTI["source"]
         sms = C.c_int()
         _abi.check(lib.rvmc_device_info(local, C.byref(sms), None, None, None))
         clk_hz = 1e6 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
