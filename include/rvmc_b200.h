@@ -253,6 +253,21 @@ RVMC_API int rvmc_unpack_bits_host(const uint32_t* bits_host, int64_t bits_strid
                           int64_t n_cols, uint8_t* out_host, int64_t out_stride, int n_threads);
 RVMC_API int rvmc_count_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, int64_t n_rows,
                          int64_t n_cols, int64_t* counts_host, int n_threads);
+/* The device-to-host leg of the packed flags in one call.  bits_dev: DEVICE uint32[n_rows][bits_stride_words]
+ * (the detected_bits of rvmc_biascorr_fused_packed); packed_host: PINNED host mirror of the same shape;
+ * out_host: the bool array, out_stride >= n_cols bytes per row.  blocks[k] = rows [row0,row1) x columns
+ * [col0,col1) (col0 a multiple of 32) with the CUDA event recorded behind the kernel launch that produced the
+ * block (or NULL: ready now).  copy_stream: a stream of its own for the copies.  Blocks are copied in the
+ * order given as soon as they are ready and widened as they land, while later blocks are still being
+ * computed; returns when out_host is complete.  Replaces the tail of get_detected_binaries
+ * (RVMC_bias_corr.py:451-476 returns `detected`). */
+typedef struct rvmc_flag_block {
+    int64_t row0, row1, col0, col1;
+    void* ready_event;          /* cudaEvent_t or NULL */
+} rvmc_flag_block;
+RVMC_API int rvmc_fetch_flags_host(const uint32_t* bits_dev, int64_t bits_stride_words, int64_t n_cols,
+                          const rvmc_flag_block* blocks, int n_blocks, void* copy_stream, uint32_t* packed_host,
+                          uint8_t* out_host, int64_t out_stride, int n_threads);
 /* memcpy with the same thread pool: moves a pinned staging block into pageable memory at DMA speed
  * (results too large to pin are staged through two fixed pinned buffers, rvmc_b200/_device.py). */
 RVMC_API int rvmc_copy_host(void* dst_host, const void* src_host, int64_t nbytes, int n_threads);

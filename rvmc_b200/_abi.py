@@ -69,6 +69,12 @@ class PointStats(C.Structure):
                [(n, C.c_uint32) for n in ("n_guard", "n_nonconverged", "n_hist_bins", "reserved")]
 
 
+class FlagBlock(C.Structure):
+    """rvmc_flag_block."""
+    _fields_ = [("row0", C.c_int64), ("row1", C.c_int64), ("col0", C.c_int64), ("col1", C.c_int64),
+                ("ready_event", C.c_void_p)]
+
+
 class GridPoint(C.Structure):
     """rvmc_grid_point."""
     _fields_ = [("pop", PopParams), ("seed", C.c_uint64)]
@@ -101,6 +107,7 @@ SIGNATURES = {
     "rvmc_unpack_bits_host": (_I, [_VP, _I64, _I64, _I64, _VP, _I64, _I]),
     "rvmc_count_bits_host": (_I, [_VP, _I64, _I64, _I64, _VP, _I]),
     "rvmc_copy_host": (_I, [_VP, _VP, _I64, _I]),
+    "rvmc_fetch_flags_host": (_I, [_VP, _I64, _I64, C.POINTER(FlagBlock), _I, _VP, _VP, _VP, _I64, _I]),
     "rvmc_biascorr_sample": (_I, [C.POINTER(PopParams), _U64, _I, _I, _VP, _VP, _U64, _I64, _U32, OrbitSoA, _VP]),
     "rvmc_kepler_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "rvmc_rv_epochs_f64": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -214,38 +214,15 @@ def unpack_bits_overlapped(bits, n_cols, chunks, threads=None):
     cs = _copy_stream(bits.device)
     packed = t.empty(bits.shape, dtype=bits.dtype, pin_memory=True)
     out = _host_result((nrows, n_cols), t.uint8)
-    done = []
-    with t.cuda.stream(cs):
-        for r0, r1, c0, c1, ev in chunks:
-            assert c0 % 32 == 0
-            cs.wait_event(ev)
-            _copy_block(packed, bits, r0, r1, c0 // 32, (c1 + 31) // 32)
-            e = t.cuda.Event()
-            e.record(cs)
-            done.append(e)
-    p_ptr, o_ptr = packed.data_ptr(), out.data_ptr()
-    k, n = 0, len(chunks)
-    while k < n:
-        with span("flags.wait_copy"):
-            done[k].synchronize()
-        # the GPU usually runs ahead of the widening: take every following block whose copy has also landed
-        # and that continues this one (next rows of the same columns, or next columns of the same rows) in
-        # ONE call -- fewer wake-ups of the helper threads, longer streaming runs
-        r0, r1, c0, c1, _ = chunks[k]
-        m = k + 1
-        while m < n and done[m].query():
-            q0, q1, d0, d1, _ = chunks[m]
-            if (d0, d1) == (c0, c1) and q0 == r1:
-                r1 = q1
-            elif (q0, q1) == (r0, r1) and d0 == c1:
-                c1 = d1
-            else:
-                break
-            m += 1
-        with span("flags.widen"):
-            _abi.check(lib.rvmc_unpack_bits_host(p_ptr + 4 * (r0 * nwords + c0 // 32), nwords, r1 - r0, c1 - c0,
-                                                 o_ptr + r0 * n_cols + c0, n_cols, threads))
-        k = m
+    blocks = (_abi.FlagBlock * len(chunks))()
+    for k, (r0, r1, c0, c1, ev) in enumerate(chunks):
+        blocks[k].row0, blocks[k].row1, blocks[k].col0, blocks[k].col1 = r0, r1, c0, c1
+        blocks[k].ready_event = ev.cuda_event
+    # one library call does the rest (waits, copies, widening) without a Python loop in the way; ctypes
+    # releases the GIL for its duration
+    with DeviceGuard(bits.device), span("flags.fetch"):
+        _abi.check(lib.rvmc_fetch_flags_host(bits.data_ptr(), nwords, n_cols, blocks, len(chunks), cs.cuda_stream,
+                                             packed.data_ptr(), out.data_ptr(), n_cols, threads))
     return out.numpy().view(np.bool_)
 
 

@@ -11,6 +11,7 @@
 // Bit order: bit j of word w of a row is column 32 w + j (what __ballot_sync produces for 32
 // consecutive samples).  On a little-endian host the words are a byte stream in which bit j of byte
 // k is column 8 k + j, i.e. np.unpackbits(..., bitorder="little").
+#include <cuda_runtime.h>
 #include <emmintrin.h>   // SSE2: baseline of every x86-64 CPU (streaming stores)
 #include <immintrin.h>   // AVX-512 path, selected at run time
 #include <pthread.h>
@@ -323,6 +324,85 @@ int rvmc_unpack_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, 
     if (n_threads > 64) n_threads = 64;
     pool().run(n_rows * j.segs_per_row, n_threads, unpack_task, &j);
     return RVMC_OK;
+}
+
+// The whole device-to-host leg of the packed flags in ONE call, without a host-language loop in the way:
+// for every block (rows x columns of the [n_rows][bits_stride] device array, in the order given) the copy
+// stream waits for the block's `ready` event (recorded behind the kernel that produced it), copies its words
+// into the pinned mirror `packed_host`, and as copies land the calling thread and the helper pool widen them
+// into `out_host` -- consecutive blocks that have landed together go out as one widening call.  Returns when
+// every flag is in place.  The GPU keeps computing later blocks meanwhile; nothing here touches the SMs.
+int rvmc_fetch_flags_host(const uint32_t* bits_dev, int64_t bits_stride_words, int64_t n_cols,
+                          const rvmc_flag_block* blocks, int n_blocks, void* copy_stream, uint32_t* packed_host,
+                          uint8_t* out_host, int64_t out_stride, int n_threads) {
+    if (n_blocks < 0 || n_cols < 0 || (n_blocks > 0 && (!bits_dev || !blocks || !packed_host || !out_host))) {
+        rvmc::set_error("rvmc_fetch_flags_host: bad arguments");
+        return RVMC_ERR_INVALID;
+    }
+    if (bits_stride_words < (n_cols + 31) / 32 || out_stride < n_cols) {
+        rvmc::set_error("rvmc_fetch_flags_host: a row stride is shorter than the row");
+        return RVMC_ERR_INVALID;
+    }
+    for (int k = 0; k < n_blocks; ++k) {
+        const rvmc_flag_block& b = blocks[k];
+        if (b.row0 < 0 || b.row1 < b.row0 || b.col0 < 0 || b.col1 < b.col0 || b.col1 > n_cols || (b.col0 & 31)) {
+            rvmc::set_error("rvmc_fetch_flags_host: block %d is malformed (columns must start on a multiple of 32)", k);
+            return RVMC_ERR_INVALID;
+        }
+    }
+    cudaStream_t cs = static_cast<cudaStream_t>(copy_stream);
+    std::vector<cudaEvent_t> done((size_t)n_blocks, nullptr);
+    cudaError_t err = cudaSuccess;
+    auto fail = [&](const char* what) {
+        rvmc::set_error("rvmc_fetch_flags_host: %s: %s", what, cudaGetErrorString(err));
+        cudaStreamSynchronize(cs);                    // nothing of ours may still be in flight into packed_host
+        for (cudaEvent_t e : done)
+            if (e) cudaEventDestroy(e);
+        cudaGetLastError();
+        return (int)err;
+    };
+    for (int k = 0; k < n_blocks; ++k) {
+        const rvmc_flag_block& b = blocks[k];
+        if (b.ready_event && (err = cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(b.ready_event), 0)) != cudaSuccess)
+            return fail("cudaStreamWaitEvent");
+        const int64_t w0 = b.col0 >> 5, w1 = (b.col1 + 31) >> 5, rows = b.row1 - b.row0;
+        if (rows > 0 && w1 > w0) {
+            const size_t off = (size_t)b.row0 * bits_stride_words + w0;
+            if (w0 == 0 && w1 == bits_stride_words)
+                err = cudaMemcpyAsync(packed_host + off, bits_dev + off, (size_t)rows * bits_stride_words * 4,
+                                      cudaMemcpyDeviceToHost, cs);
+            else
+                err = cudaMemcpy2DAsync(packed_host + off, (size_t)bits_stride_words * 4, bits_dev + off,
+                                        (size_t)bits_stride_words * 4, (size_t)(w1 - w0) * 4, (size_t)rows,
+                                        cudaMemcpyDeviceToHost, cs);
+            if (err != cudaSuccess) return fail("cudaMemcpyAsync");
+        }
+        if ((err = cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate");
+        if ((err = cudaEventRecord(done[k], cs)) != cudaSuccess) return fail("cudaEventRecord");
+    }
+    int rc = RVMC_OK;
+    for (int k = 0; k < n_blocks && rc == RVMC_OK;) {
+        if ((err = cudaEventSynchronize(done[k])) != cudaSuccess) return fail("cudaEventSynchronize");
+        int64_t r0 = blocks[k].row0, r1 = blocks[k].row1, c0 = blocks[k].col0, c1 = blocks[k].col1;
+        int m = k + 1;
+        // the GPU usually runs ahead of the widening: take every following block that has also landed and
+        // continues this one (next rows of the same columns, or next columns of the same rows)
+        while (m < n_blocks && cudaEventQuery(done[m]) == cudaSuccess) {
+            const rvmc_flag_block& q = blocks[m];
+            if (q.col0 == c0 && q.col1 == c1 && q.row0 == r1) r1 = q.row1;
+            else if (q.row0 == r0 && q.row1 == r1 && q.col0 == c1) c1 = q.col1;
+            else break;
+            ++m;
+        }
+        cudaGetLastError();                              // cudaEventQuery leaves cudaErrorNotReady behind
+        if (r1 > r0 && c1 > c0)
+            rc = rvmc_unpack_bits_host(packed_host + (size_t)r0 * bits_stride_words + (c0 >> 5), bits_stride_words,
+                                       r1 - r0, c1 - c0, out_host + (size_t)r0 * out_stride + c0, out_stride, n_threads);
+        k = m;
+    }
+    for (cudaEvent_t e : done)
+        if (e) cudaEventDestroy(e);
+    return rc;
 }
 
 int rvmc_count_bits_host(const uint32_t* bits_host, int64_t bits_stride_words, int64_t n_rows, int64_t n_cols,
