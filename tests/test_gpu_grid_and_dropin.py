@@ -238,6 +238,28 @@ def test_fast_statistics_kernel_equals_the_general_one_and_numpy(bin, monkeypatc
                 assert fast["stats"]["mode"][i] == edges[int(np.argmax(cnt))] + bin / 2
 
 
+def test_fast_statistics_kernel_hands_over_rows_with_crowded_target_bins(monkeypatch):
+    """With 1.5e6 realizations per point the 16-bit-prefix bins around the percentiles hold more values than
+    the fast kernel's candidate list (16 384): it must hand the row to the general kernel, and the call must
+    return the same statistics as the general kernel alone and as NumPy."""
+    pops = [_abi.PopParams.defaults(fbin=0.7), _abi.PopParams.defaults(fbin=0.3, min_period=30.0)]
+    n_real = 1_500_000
+    monkeypatch.delenv("RVMC_STATS_GENERAL", raising=False)
+    fast = grid.run_points(pops, [5, 6], M17, 12, n_real, keep_sigma=True, distributed=False)
+    monkeypatch.setenv("RVMC_STATS_GENERAL", "1")
+    gen = grid.run_points(pops, [5, 6], M17, 12, n_real, keep_sigma=True, distributed=False)
+    monkeypatch.delenv("RVMC_STATS_GENERAL", raising=False)
+    for k in grid.STATS_DTYPE.names:
+        if k == "mean":
+            np.testing.assert_allclose(fast["stats"][k], gen["stats"][k], rtol=1e-13, atol=0)
+        else:
+            np.testing.assert_array_equal(fast["stats"][k], gen["stats"][k], err_msg=k)
+    for i in range(2):
+        sig = fast["sigma"][i].astype(np.float64)
+        assert fast["stats"]["median"][i] == np.median(sig) and fast["stats"]["p95"][i] == np.percentile(sig, 95)
+        assert abs(fast["stats"]["mean"][i] / sig.mean() - 1) < 1e-12
+
+
 def test_grid_per_point_failure_counters_and_best_fit_ignores_nan():
     """rvmc_point_stats.n_guard / n_nonconverged are filled per point by the producer kernels (what
     scipy.optimize.newton reports per call, RVMC.py:177-180): with eccentricities up to 0.999 the fp64
