@@ -355,3 +355,63 @@ def test_flag_transfer_resolution_range_weights_and_host_threads(monkeypatch):
     assert dv.host_threads() == 1
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
     assert 1 <= dv.host_threads() <= 8
+
+
+def test_grid_search_builds_only_the_ranks_share(monkeypatch):
+    """grid_search must hand each rank exactly its own records (SURVEY 8e / VERDICT r1: O(points / world) host
+    work): the records a rank builds equal the rows of the full Cartesian table it owns, with the point's grid
+    index as its random substream, for the fused f_bin axis and for independent cells, at several world sizes.
+    No GPU: run_points / run_points_fbins are replaced by recorders."""
+    from rvmc_b200 import grid
+    axes = dict(period_pi=np.linspace(-0.9, 0.4, 5), mass_ratio_kappa=np.linspace(-0.9, 0.9, 3),
+                fbin=np.linspace(0.25, 1.0, 4))
+    names = list(axes)
+    full_mesh = np.meshgrid(*axes.values(), indexing="ij")
+    full = grid.points_array(60, **{k: m.ravel() for k, m in zip(names, full_mesh)})
+    other = np.meshgrid(axes["period_pi"], axes["mass_ratio_kappa"], indexing="ij")
+    calls = {}
+
+    def fake_points(pops, seeds, errs, S, n, **kw):
+        calls["points"] = (pops.copy(), kw["local"].copy(), kw["n_points"])
+        return dict(stats=np.zeros(kw["n_points"], dtype=grid.STATS_DTYPE), counters=np.zeros(4, np.int64),
+                    local=kw["local"])
+
+    def fake_fbins(pops, seeds, fbins, errs, S, n, **kw):
+        calls["fbins"] = (pops.copy(), kw["local"].copy(), kw["n_points"], np.asarray(fbins))
+        return dict(stats=np.zeros((kw["n_points"], len(fbins)), dtype=grid.STATS_DTYPE),
+                    counters=np.zeros(4, np.int64), local=kw["local"])
+
+    monkeypatch.setattr(grid, "run_points", fake_points)
+    monkeypatch.setattr(grid, "run_points_fbins", fake_fbins)
+    owned_indep, owned_fused = [], []
+    for world in (1, 3, 8):
+        for rank in range(world):
+            monkeypatch.setattr(grid, "dist_info", lambda group=None, r=rank, w=world: (r, w))
+            out = grid.grid_search(axes, number_of_samples=10, seed=7, share_fbin_draws=False, observed_sigma=5.0)
+            pops, local, n_points = calls["points"]
+            assert n_points == 60 and out["shape"] == (5, 3, 4) and len(pops) == len(local)
+            for k in names:
+                np.testing.assert_array_equal(pops[k], full[k][local])
+            np.testing.assert_array_equal(pops["substream"], local.astype(np.uint32))
+            assert np.all(pops["seed"] == 7)
+            if world == 8:
+                owned_indep.append(local)
+                # every rank holds each binary fraction (the cost level) the same number of times, to within one
+                counts = np.bincount(np.searchsorted(axes["fbin"], pops["fbin"]), minlength=4)
+                assert counts.max() - counts.min() <= 1
+            out = grid.grid_search(axes, number_of_samples=10, seed=7, observed_sigma=5.0)
+            pops, local, n_points, fb = calls["fbins"]
+            assert n_points == 15 and out["fbin_axis_fused"]
+            np.testing.assert_array_equal(fb, axes["fbin"])
+            np.testing.assert_array_equal(pops["period_pi"], other[0].ravel()[local])
+            np.testing.assert_array_equal(pops["mass_ratio_kappa"], other[1].ravel()[local])
+            np.testing.assert_array_equal(pops["substream"], local.astype(np.uint32))
+            if world == 8:
+                owned_fused.append(local)
+    np.testing.assert_array_equal(np.sort(np.concatenate(owned_indep)), np.arange(60))
+    np.testing.assert_array_equal(np.sort(np.concatenate(owned_fused)), np.arange(15))
+    # an index of -1 on an axis raises before anything is built or launched (RVMC.py:112)
+    calls.clear()
+    with pytest.raises(ZeroDivisionError):
+        grid.grid_search(dict(period_pi=np.array([-1.0, 0.0]), fbin=np.array([0.5])), number_of_samples=10)
+    assert not calls
