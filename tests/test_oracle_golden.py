@@ -151,3 +151,53 @@ def test_best_fit_indices_first_strict_minimum():
     flat = [200.0] * 5                       # never closer than the initial 100 -> index stays 0
     idx = orc.best_fit_indices(10.0, med, med, flat, med, med, med)
     assert idx == (2, 0, 2, 2, 2)
+
+
+def test_oracle_distributions_vs_five_independent_reference_runs(golden_dir):
+    """The oracle as a MODEL (not only as arithmetic on recorded draws): driven by NumPy's own generator it
+    must produce the sigma_1D and Delta-RV DISTRIBUTIONS the unmodified reference produces
+    (tests/golden/reference_multiseed.npz: five independent reference runs, 10^7-star pools -- the infinite-pool
+    limit the fused GPU kernels implement).  Two-sample KS, Bonferroni over the 15 comparisons (SURVEY H2 iii)."""
+    from scipy import stats as sps
+    z = np.load(os.path.join(golden_dir, "reference_multiseed.npz"), allow_pickle=False)
+    m17 = z["m17_errors"]
+    days = np.array([0, 1, 7, 30, 180, 365.0]) * 86400
+    pvals = []
+    for tag, fbin in (("fbin070_pmin14", 0.7), ("fbin028_pmin14", 0.28)):
+        rng = np.random.RandomState(12345)
+        n_real, S = 20000, 12
+        n = n_real * S
+        m1 = orc.masses_from_uniform(rng.random_sample(n), 6., 20., -2.35)
+        per = orc.period_from_uniform(rng.random_sample(n), 1.4, 3500., -0.5)
+        t = orc.time_from_uniform(rng.random_sample(n), per)
+        q = orc.mass_ratio_from_uniform(rng.random_sample(n), 0.1, 1.0, 0)
+        e = orc.eccentricity_from_uniform_slotted(per, rng.random_sample(n), -0.5)
+        inc = orc.inclination_from_uniform(rng.random_sample(n))
+        om = orc.orbit_rotation_from_uniform(rng.random_sample(n))
+        E = orc.eccentric_anomaly_single_epoch(t, per, e)
+        rv = orc.orbital_rv(m1, per, q, e, inc, om, E)
+        is_bin = rng.random_sample(n) < fbin
+        v = np.where(is_bin, rv, 0.0) + rng.normal(0, 2.0, n) + rng.normal(0, np.tile(m17, n_real), n)
+        ours = orc.sigma1d_unweighted(v.reshape(n_real, S), ddof=1)
+        for k in range(z["sigma_" + tag].shape[0]):
+            pvals.append(sps.ks_2samp(ours, z["sigma_" + tag][k].astype(np.float64)).pvalue)
+    rng = np.random.RandomState(777)
+    ns = 20000
+    m1 = orc.masses_from_uniform(rng.random_sample(ns), 6., 20., -2.35)
+    per = orc.period_from_uniform(rng.random_sample(ns), 10 ** 0.15, 10 ** 3.5, -0.5)
+    t = orc.time_from_uniform(rng.random_sample(ns), per)
+    q = orc.mass_ratio_from_uniform(rng.random_sample(ns), 0.1, 1.0, 0)
+    e = orc.eccentricity_from_uniform_slotted(per, rng.random_sample(ns), -0.5)
+    inc = orc.inclination_from_uniform(rng.random_sample(ns))
+    om = orc.orbit_rotation_from_uniform(rng.random_sample(ns))
+    rvs = orc.multi_epoch_rv(days, t, per, e, q, m1, inc, om) + rng.normal(0, 2.0, (6, ns))
+    drv = orc.delta_rv(rvs)
+    frac = orc.detected_binaries(rvs, 2.0, 20, 4).mean()
+    for k in range(z["biascorr_delta_rv"].shape[0]):
+        pvals.append(sps.ks_2samp(drv, z["biascorr_delta_rv"][k].astype(np.float64)).pvalue)
+    ps = np.array(pvals)
+    assert len(ps) == 15 and ps.min() > 0.01 / len(ps), np.sort(ps)[:3]
+    assert np.median(ps) > 0.1, np.sort(ps)
+    p_ref = float(np.mean(z["biascorr_detected_fraction"]))
+    se = np.sqrt(p_ref * (1 - p_ref) * (1 / 50000 + 1 / ns))
+    assert abs(frac - p_ref) < 4 * se
