@@ -338,6 +338,19 @@ RVMC_API int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points
                         double bin, int hist_bins, rvmc_point_stats* stats_out, float* sigma_out,
                         uint32_t* hist_out, float* scratch, uint64_t* counters, void* cuda_stream);
 
+/* HOST helper of the grid fit (no GPU work; stats_host is a HOST pointer): ONE pass over a table of
+ * n_points records in grid (C) order.
+ *   best fit -- findBestDistributions.py:138-158: the FIRST strict minimum of |central - observed| below the
+ *     initial distance of 100, central = median (use_mode == 0) or mode; a NaN is never selected; nothing
+ *     below 100 leaves best_index 0 and best_distance 100.  Skipped when have_observed == 0.
+ *   totals[4] -- sums of `reserved` (points whose histogram the statistics kernel could not hold),
+ *     `n_nonconverged`, the number of points with n_nonconverged != 0 (SciPy's RuntimeWarning at
+ *     RVMC.py:177-180 is per call) and `n_guard`.
+ * Any output pointer may be NULL.  Up to n_threads threads of the library's host pool. */
+RVMC_API int rvmc_grid_best_fit_host(const rvmc_point_stats* stats_host, int64_t n_points, int use_mode,
+                            int have_observed, double observed, int64_t* best_index, double* best_distance,
+                            uint64_t* totals, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

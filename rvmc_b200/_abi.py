@@ -119,6 +119,8 @@ SIGNATURES = {
                                  _VP, _VP, _VP, _VP, _VP, _VP]),
     "rvmc_grid_run": (_I, [C.POINTER(GridPoint), _I64, _VP, _I, _I, _I, _I64, _D, _I, _VP, _VP, _VP, _VP,
                            _VP, _VP]),
+    "rvmc_grid_best_fit_host": (_I, [_VP, _I64, _I, _I, _D, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_uint64), _I]),
 }
 
 _lib = None

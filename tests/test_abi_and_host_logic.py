@@ -415,3 +415,68 @@ def test_grid_search_builds_only_the_ranks_share(monkeypatch):
     with pytest.raises(ZeroDivisionError):
         grid.grid_search(dict(period_pi=np.array([-1.0, 0.0]), fbin=np.array([0.5])), number_of_samples=10)
     assert not calls
+
+
+def test_table_summary_is_the_reference_best_fit_rule_in_one_pass(monkeypatch):
+    """rvmc_grid_best_fit_host (host code, no GPU): the best-fit rule of findBestDistributions.py:138-158 -- first
+    strict minimum below the initial distance of 100, NaNs never win -- and the table's sanity totals, in one pass
+    over the 80-byte records; checked against best_fit_indices (the Python statement of the rule) and against the
+    NumPy gathers it replaces, for ties, NaNs, nothing-below-100 and every thread count; then through grid_search
+    for a C-ordered table (native pass) and for one whose fused f_bin axis is not the last (NumPy fallback)."""
+    from rvmc_b200 import grid
+    rng = np.random.default_rng(11)
+    for n in (1, 7, 4096, 4097, 65536 + 13):
+        st = np.zeros(n, dtype=grid.STATS_DTYPE)
+        st["median"] = rng.uniform(5, 60, n)
+        st["mode"] = np.round(rng.uniform(5, 60, n) * 2) / 2 + 0.25          # many exact ties, like real modes
+        st["median"][rng.random(n) < 0.1] = np.nan
+        st["n_nonconverged"] = rng.integers(0, 3, n) * (rng.random(n) < 0.01)
+        st["n_guard"] = rng.integers(0, 5, n)
+        z = np.zeros(n)
+        for usemode in (False, True):
+            for obs in (25.0, 25.25, -200.0, 1e4):
+                idx, dist, tot = grid.table_summary(st, obs, usemode)
+                want = grid.best_fit_indices(obs, st["mode"], st["median"], z, z, z, z, usemode=usemode)[0]
+                assert idx == want, (n, usemode, obs)
+                c = st["mode" if usemode else "median"][idx]
+                assert dist == (abs(c - obs) if abs(c - obs) < 100 else 100.0)
+                assert tot == (0, int(st["n_nonconverged"].sum()), int(np.count_nonzero(st["n_nonconverged"])),
+                               int(st["n_guard"].sum()))
+        for threads in (1, 2, 5):
+            monkeypatch.setenv("RVMC_HOST_THREADS", str(threads))
+            assert grid.table_summary(st, 25.0)[0] == grid.best_fit_indices(25.0, st["mode"], st["median"], z, z, z, z)[0]
+        monkeypatch.delenv("RVMC_HOST_THREADS")
+    st = np.zeros(10, dtype=grid.STATS_DTYPE)
+    st["median"] = np.nan
+    assert grid.table_summary(st, 25.0)[:2] == (0, 100.0)                   # nothing qualifies: index 0, distance 100
+    assert grid.table_summary(st)[2] == (0, 0, 0, 0)                         # totals only
+    assert grid.table_summary(st[::2]) is None                               # not C-contiguous: caller falls back
+    assert grid.table_summary(np.zeros(0, dtype=grid.STATS_DTYPE), 1.0)[:2] == (0, 100.0)
+    st["reserved"][3] = 1
+    with pytest.raises(NotImplementedError):
+        grid._finish(st)
+    st["reserved"][3] = 0
+    st["n_nonconverged"][[2, 5]] = (3, 4)
+    with pytest.warns(RuntimeWarning, match=r"7 orbits in 2 grid points"):
+        grid._finish(st)
+    with pytest.warns(RuntimeWarning, match=r"7 orbits in 2 grid points"):
+        grid._finish(st[::1], totals=None)
+
+    # through grid_search: fbin last (C-ordered table, native pass) and fbin first (moveaxis -> NumPy fallback)
+    def fake_fbins(pops, seeds, fbins, errs, S, n, **kw):
+        assert kw["finish"] is False                  # grid_search folds the checks into its own pass
+        t = np.zeros((kw["n_points"], len(fbins)), dtype=grid.STATS_DTYPE)
+        t["median"] = 10.0 + np.arange(t.size).reshape(t.shape) % 17
+        t["median"][0, 0] = np.nan
+        return dict(stats=t, counters=np.zeros(4, np.int64), local=kw["local"])
+    monkeypatch.setattr(grid, "run_points_fbins", fake_fbins)
+    monkeypatch.setattr(grid, "dist_info", lambda group=None: (0, 1))
+    for order in (("period_pi", "fbin"), ("fbin", "period_pi")):
+        axes = {k: (np.linspace(-0.9, 0.4, 6) if k == "period_pi" else np.linspace(0.25, 1.0, 4)) for k in order}
+        out = grid.grid_search(axes, number_of_samples=10, seed=7, observed_sigma=13.0)
+        med = out["stats"]["median"]
+        assert med.shape == out["shape"] == tuple(len(axes[k]) for k in order)
+        d = np.abs(med - 13.0)
+        d[np.isnan(d)] = np.inf
+        assert out["best_index"] == tuple(int(v) for v in np.unravel_index(np.argmin(d), med.shape))
+        assert out["best_distance"] == 0.0
