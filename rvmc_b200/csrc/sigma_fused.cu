@@ -242,9 +242,11 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
     __shared__ unsigned int cnt_guard, cnt_bad;
     __shared__ unsigned int fail_k[2 * FBINS_MAX];       // per fraction: guard lanes, non-converged lanes
 
-    const int64_t tile = blockIdx.x;
-    const int64_t point = tile / a.tiles_per_point;
-    const int64_t r0 = (tile - point * a.tiles_per_point) * a.R;
+    // 32-bit division: a launch holds < 2^31 tiles (checked on the host); the 64-bit one costs ~70 instructions
+    const uint32_t tile = blockIdx.x;
+    const uint32_t point_u = tile / (uint32_t)a.tiles_per_point;
+    const int64_t point = point_u;
+    const int64_t r0 = (int64_t)(tile - point_u * (uint32_t)a.tiles_per_point) * a.R;
     const int nr = (int)min((int64_t)a.R, a.n_real - r0);
     const int nslots = nr * S;
     {
@@ -359,17 +361,26 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         // with the eight accumulator pairs in registers; same operations in the same order as the generic
         // reducer.  Items are dealt group-major, so a warp holds 32 consecutive realizations of one group
         // (coalesced stores); the host sizes the tile so that the items fill the block's threads.
+        // Everything around the sweep is kept off the per-item path (it was 11 % of the kernel's instructions,
+        // profiles/r02_grid_kernels_hot_lines.txt): no integer division for (group, realization), thresholds
+        // padded with zeros by the host instead of eight bounds tests, one output pointer walked by the row
+        // stride instead of eight 64-bit index products, and unconditional stores for a full group.
         const int ngroups = (fa.n_fbins + 7) >> 3;
         const SigmaNorm<float> norm(S, a.ddof);
-        for (int item = threadIdx.x; item < nr * ngroups; item += blockDim.x) {
-            const int grp = item / nr;
-            const int r = item - grp * nr;
+        const int nitems = nr * ngroups;
+        float* const out_tile = a.sigma_out + (size_t)point * fa.n_fbins * a.sigma_stride + r0;
+        for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
+            int grp = 0, r = item;
+            while (r >= nr) {                    // ngroups <= FBINS_MAX / 8 = 4
+                r -= nr;
+                ++grp;
+            }
             const int k0 = grp << 3;
             const int base = r * S;
             float s1[8], s2[8], pivot[8];
             uint32_t thr[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) thr[k] = (k0 + k < fa.n_fbins) ? fa.thresh[k0 + k] : 0u;
+            for (int k = 0; k < 8; ++k) thr[k] = fa.thresh[k0 + k];      // 0 beyond n_fbins: never a binary, never stored
             {
                 const float nz = noise[base], both = nz + rv[base];
                 const uint32_t c = coin[base];
@@ -390,11 +401,15 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
                     s2[k] = fmaf(d, d, s2[k]);
                 }
             }
+            float* o = out_tile + (size_t)k0 * a.sigma_stride + r;
+            if (k0 + 8 <= fa.n_fbins) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k0 + k < fa.n_fbins)
-                    a.sigma_out[(point * fa.n_fbins + k0 + k) * a.sigma_stride + r0 + r] =
-                        sigma_from_sums(s1[k], s2[k], norm);
+                for (int k = 0; k < 8; ++k, o += a.sigma_stride) *o = sigma_from_sums(s1[k], s2[k], norm);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k, o += a.sigma_stride)
+                    if (k0 + k < fa.n_fbins) *o = sigma_from_sums(s1[k], s2[k], norm);
+            }
         }
     } else
     for (int k = 0; k < fa.n_fbins; ++k) {
@@ -1432,6 +1447,7 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
     FbinArgs fa;
     fa.n_fbins = n_fbins;
     fa.thresh_max = 0;
+    for (int k = 0; k < FBINS_MAX; ++k) fa.thresh[k] = 0;       // the kernel reads whole groups of eight
     for (int k = 0; k < n_fbins; ++k) {
         RVMC_REQUIRE(fbins[k] >= 0.0 && fbins[k] <= 1.0, "fbin must be in [0,1] (got %g)", fbins[k]);
         fa.thresh[k] = (uint32_t)llrint(fbins[k] * 16777216.0);
