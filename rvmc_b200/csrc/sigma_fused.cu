@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256, SINGLE ? 3 : 4) sigma1d_fused_kernel(Fuse
 // same seed (same integer coin compare, same fp32 adds, same reduction order), so this is purely an
 // execution strategy: an n_f-point axis costs about as much as its f_bin = max point alone.
 #define FBINS_MAX 32
+#define FB_THREADS 256          // block size as a compile-time constant: the loops' trip counts need no division
 struct FbinArgs {
     FusedArgs base;                 // points: one descriptor per (other-axes) point; coin_thresh unused
     int32_t n_fbins;
@@ -225,7 +226,7 @@ struct FbinArgs {
 };
 
 template <bool KEYED, int ITERS, bool GUARD>
-__global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa) {
+__global__ void __launch_bounds__(FB_THREADS, 4) sigma1d_fused_fbins_kernel(FbinArgs fa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FusedArgs& a = fa.base;
     const int S = a.S;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.points + point);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&pt);
-        for (int i = threadIdx.x; i < (int)(sizeof(FusedPoint) / 4); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(FusedPoint) / 4); i += FB_THREADS) dst[i] = src[i];
     }
     if (threadIdx.x < 2 * FBINS_MAX) fail_k[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         cnt_bad = 0;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    for (int j = threadIdx.x; j < S; j += FB_THREADS) {
         const float e = a.meas_err[j];
         scale[j] = slot_scale(pt.pop.sigma_dyn, e);
         wts[j] = 1.0f / (e * e);
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
 
     // ---- phase A: coins + noise (as sigma1d_fused_kernel, the coin itself is kept) ---------------
     const int npairs_pad = (npairs + 31) & ~31;
-    for (int pi = threadIdx.x; pi < npairs_pad; pi += blockDim.x) {
+    for (int pi = threadIdx.x; pi < npairs_pad; pi += FB_THREADS) {
         bool bin0 = false, bin1 = false;
         int l0 = 0, l1 = 0;
         if (pi < npairs) {
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
     // ---- phase B: one orbit per slot that is a binary under the largest fraction -------------------
     const int nq = all_binaries ? nslots : qn;
     unsigned int my_guard = 0, my_bad = 0;
-    for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+    for (int k = threadIdx.x; k < nq; k += FB_THREADS) {
         const int l = all_binaries ? k : queue[k];
         RVMC_DEV_ASSERT(l >= 0 && l < nslots);
         const uint64_t slot = slot0 + (uint64_t)l;
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(256, 4) sigma1d_fused_fbins_kernel(FbinArgs fa
         const SigmaNorm<float> norm(S, a.ddof);
         const int nitems = nr * ngroups;
         float* const out_tile = a.sigma_out + (size_t)point * fa.n_fbins * a.sigma_stride + r0;
-        for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
+        for (int item = threadIdx.x; item < nitems; item += FB_THREADS) {
             int grp = 0, r = item;
             while (r >= nr) {                    // ngroups <= FBINS_MAX / 8 = 4
                 r -= nr;
@@ -1526,7 +1527,7 @@ int rvmc_grid_run_fbins(const rvmc_grid_point* points, int64_t n_points, const d
                                   "smem attr");
             if (rc2) return rc2;
         }
-        kernel<<<total, 256, smem, stream>>>(fa);
+        kernel<<<total, FB_THREADS, smem, stream>>>(fa);
         return cuda_status(cudaGetLastError(), "sigma1d_fused_fbins_kernel launch");
     };
     int64_t nb = 0;
