@@ -246,6 +246,10 @@ def test_hot_kernels_resource_usage_and_instruction_mix(lib):
     assert len(single) == 1 and usage[single[0]][0] <= 64 and usage[single[0]][1] == 0, usage[single[0]]
     multi = [k for k in usage if "sigma1d_fused_kernelILb0ELb0ELi1ELb0" in k or "sigma1d_fused_kernelILb0ELb1ELi1ELb0" in k]
     assert len(multi) == 2 and all(usage[k][0] <= 64 and usage[k][1] == 0 for k in multi)   # per-point / shared key
+    # the f_bin-axis kernel of the grid: 4 blocks of 256 threads per SM need <= 64 registers, and its fast
+    # instantiations (shared / per-point key) must not spill (a per-row form of its reduction phase did, and was slower)
+    fbins = [k for k in usage if "sigma1d_fused_fbins_kernelILb1ELi1ELb0" in k or "sigma1d_fused_fbins_kernelILb0ELi1ELb0" in k]
+    assert len(fbins) == 2 and all(usage[k][0] <= 64 and usage[k][1] == 0 for k in fbins), [usage[k] for k in fbins]
     sass = subprocess.run(["cuobjdump", "-sass", _abi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     assert "IMAD.WIDE.U32" in sass and "MUFU.EX2" in sass and "MUFU.LG2" in sass and "DFMA" in sass
     for tensor_op in ("HMMA", "UTCHMMA", "UTCQMMA", "IMMA", "DMMA"):
